@@ -1,0 +1,121 @@
+// Complex helpers and fully-unrolled in-register DFTs of size 2..32 (forward sign, e^{-2 pi i jk/R}).
+// The inverse direction never needs its own butterflies: IDFT(x) = swap(DFT(swap(x))) where swap
+// exchanges re and im, so kernels swap on load / store instead (see fft_kernel.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+#include <utility>
+
+namespace b200fft {
+
+template <typename T> struct cpx_of;
+template <> struct cpx_of<float> { using type = float2; };
+template <> struct cpx_of<double> { using type = double2; };
+template <typename T> using cpx_t = typename cpx_of<T>::type;
+
+template <typename C> using real_of = decltype(C::x);
+
+// compile-time loop: static_for<0,N>([&](auto ic){ constexpr int i = ic; ... });
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(static_cast<F&&>(f));
+  }
+}
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return C{a.x + b.x, a.y + b.y}; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { return C{a.x - b.x, a.y - b.y}; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+  return C{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename C> __device__ __forceinline__ C mul_mi(C a) { return C{a.y, -a.x}; }  // a * (-i)
+template <typename C> __device__ __forceinline__ C cswap(C a) { return C{a.y, a.x}; }
+
+// cos(2 pi m / 32), m = 0..8  (first quadrant incl. end points), correctly rounded doubles
+__device__ __forceinline__ constexpr double cos32(int m) {
+  constexpr double t[9] = {1.0,
+                           0.98078528040323044912618223613424,
+                           0.92387953251128675612818318939679,
+                           0.83146961230254523707878837761791,
+                           0.70710678118654752440084436210485,
+                           0.55557023301960222474283081394853,
+                           0.38268343236508977172845998403040,
+                           0.19509032201612826784828486847702,
+                           0.0};
+  return t[m];
+}
+// real/imag part of exp(-2 pi i m / 32) for any integer m >= 0
+__device__ __forceinline__ constexpr double w32_re(int m) {
+  m &= 31;
+  if (m <= 8) return cos32(m);
+  if (m <= 16) return -cos32(16 - m);
+  if (m <= 24) return -cos32(m - 16);
+  return cos32(32 - m);
+}
+__device__ __forceinline__ constexpr double w32_im(int m) {  // -sin(2 pi m/32) = re(m + 8)
+  return w32_re(m + 8);
+}
+
+// multiply by exp(-2 pi i M / 32) with M a compile-time constant; trivial cases cost 0-2 flops
+template <int M, typename C>
+__device__ __forceinline__ C mul_w32(C a) {
+  using T = real_of<C>;
+  constexpr int m = M & 31;
+  if constexpr (m == 0) return a;
+  else if constexpr (m == 8) return C{a.y, -a.x};
+  else if constexpr (m == 16) return C{-a.x, -a.y};
+  else if constexpr (m == 24) return C{-a.y, a.x};
+  else if constexpr (m == 4) { constexpr T h = (T)0.70710678118654752440084436210485; return C{(a.x + a.y) * h, (a.y - a.x) * h}; }
+  else if constexpr (m == 12) { constexpr T h = (T)0.70710678118654752440084436210485; return C{(a.y - a.x) * h, -(a.x + a.y) * h}; }
+  else if constexpr (m == 20) { constexpr T h = (T)0.70710678118654752440084436210485; return C{-(a.x + a.y) * h, (a.x - a.y) * h}; }
+  else if constexpr (m == 28) { constexpr T h = (T)0.70710678118654752440084436210485; return C{(a.x - a.y) * h, (a.x + a.y) * h}; }
+  else {
+    constexpr T wr = (T)w32_re(m), wi = (T)w32_im(m);
+    return C{a.x * wr - a.y * wi, a.x * wi + a.y * wr};
+  }
+}
+
+// In-place forward DFT of R register-resident values, natural order in and out.
+template <int R, typename C>
+__device__ __forceinline__ void dft(C (&x)[R]) {
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "unsupported register radix");
+  if constexpr (R == 2) {
+    C a = x[0], b = x[1];
+    x[0] = cadd(a, b); x[1] = csub(a, b);
+  } else if constexpr (R == 4) {
+    C t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+    C t2 = cadd(x[1], x[3]), t3 = mul_mi(csub(x[1], x[3]));
+    x[0] = cadd(t0, t2); x[1] = cadd(t1, t3); x[2] = csub(t0, t2); x[3] = csub(t1, t3);
+  } else if constexpr (R == 8) {
+    C e[4] = {x[0], x[2], x[4], x[6]};
+    C o[4] = {x[1], x[3], x[5], x[7]};
+    dft<4>(e); dft<4>(o);
+    static_for<0, 4>([&](auto kc) {
+      constexpr int k = kc;
+      C t = mul_w32<4 * k>(o[k]);
+      x[k] = cadd(e[k], t); x[k + 4] = csub(e[k], t);
+    });
+  } else if constexpr (R >= 16) {
+    constexpr int M = R / 4;
+    C s0[M], s1[M], s2[M], s3[M];
+    static_for<0, M>([&](auto mc) {
+      constexpr int m = mc;
+      s0[m] = x[4 * m]; s1[m] = x[4 * m + 1]; s2[m] = x[4 * m + 2]; s3[m] = x[4 * m + 3];
+    });
+    dft<M>(s0); dft<M>(s1); dft<M>(s2); dft<M>(s3);
+    static_for<0, M>([&](auto kc) {
+      constexpr int k = kc;
+      constexpr int u = 32 / R;  // w_R^m = w_32^(m*u)
+      C a0 = s0[k];
+      C a1 = mul_w32<u * k>(s1[k]);
+      C a2 = mul_w32<2 * u * k>(s2[k]);
+      C a3 = mul_w32<3 * u * k>(s3[k]);
+      C t0 = cadd(a0, a2), t1 = csub(a0, a2);
+      C t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+      x[k] = cadd(t0, t2); x[k + M] = cadd(t1, t3); x[k + 2 * M] = csub(t0, t2); x[k + 3 * M] = csub(t1, t3);
+    });
+  }
+}
+
+}  // namespace b200fft

@@ -1,0 +1,363 @@
+// Non power-of-two axis lengths.  See generic.h.
+#include "generic.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "cplx.cuh"
+
+namespace b200fft {
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+template <typename C>
+__global__ void copy_scale_kernel(const C* __restrict__ in, C* __restrict__ out, long long n, real_of<C> scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    C v = in[i];
+    v.x *= scale; v.y *= scale;
+    out[i] = v;
+  }
+}
+
+// Bluestein step 1: A[l][m] = x_l[m] * chirp[m] (m < N), 0 (N <= m < M); line l0+l = (o, i)
+template <typename C>
+__global__ void chirp_pack_kernel(const C* __restrict__ in, C* __restrict__ A, const C* __restrict__ chirp, long long N,
+                                  long long I, long long M, long long l0, long long nl, int swap_in) {
+  const long long total = nl * M;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    // consecutive threads -> consecutive lines when the axis is strided (coalesced reads), else consecutive m
+    long long l, m;
+    if (I > 1) { l = idx % nl; m = idx / nl; } else { m = idx % M; l = idx / M; }
+    C v = C{0, 0};
+    if (m < N) {
+      const long long line = l0 + l, o = line / I, i = line % I;
+      v = in[o * N * I + m * I + i];
+      if (swap_in) v = cswap(v);
+      v = cmul(v, chirp[m]);
+    }
+    A[l * M + m] = v;
+  }
+}
+
+template <typename C>
+__global__ void filt_mul_kernel(C* __restrict__ B, const C* __restrict__ filt, long long M, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    B[idx] = cmul(B[idx], filt[idx % M]);
+}
+
+// Bluestein step 5: out_l[k] = A[l][k] * chirp[k] * scale
+template <typename C>
+__global__ void chirp_unpack_kernel(const C* __restrict__ A, C* __restrict__ out, const C* __restrict__ chirp, long long N,
+                                    long long I, long long M, long long l0, long long nl, int swap_out, real_of<C> scale) {
+  const long long total = nl * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long l, k;
+    if (I > 1) { l = idx % nl; k = idx / nl; } else { k = idx % N; l = idx / N; }
+    C v = cmul(A[l * M + k], chirp[k]);
+    v.x *= scale; v.y *= scale;
+    if (swap_out) v = cswap(v);
+    const long long line = l0 + l, o = line / I, i = line % I;
+    out[o * N * I + k * I + i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mixed-radix Stockham in shared memory, runtime radices (2,3,4,5,7,8 and generic odd primes <= 13)
+// tile = TL lines x N points, ping-pong buffers; twiddles from a global table w_N^m.
+// ------------------------------------------------------------------------------------------
+struct MixedParams {
+  long long O, N, I;
+  int nstages;
+  int radix[12];
+  int TL;
+  int line_fast;  // 1: adjacent threads load adjacent lines (I > 1), 0: adjacent points (I == 1)
+  int swap_in, swap_out;
+};
+
+template <int R, typename C>
+__device__ __forceinline__ void small_dft(C* a) {
+  using T = real_of<C>;
+  if constexpr (R == 2) {
+    C x = a[0], y = a[1];
+    a[0] = cadd(x, y); a[1] = csub(x, y);
+  } else if constexpr (R == 4) {
+    C t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]), t2 = cadd(a[1], a[3]), t3 = mul_mi(csub(a[1], a[3]));
+    a[0] = cadd(t0, t2); a[1] = cadd(t1, t3); a[2] = csub(t0, t2); a[3] = csub(t1, t3);
+  } else if constexpr (R == 3) {
+    const T c = (T)-0.5, s = (T)-0.86602540378443864676372317075294;  // exp(-2 pi i/3) = c + i s
+    C t = cadd(a[1], a[2]), d = csub(a[1], a[2]);
+    C m = C{a[0].x + c * t.x, a[0].y + c * t.y};
+    C r = C{-s * d.y, s * d.x};  // i*s*d
+    a[0] = cadd(a[0], t); a[1] = cadd(m, r); a[2] = csub(m, r);
+  } else if constexpr (R == 5) {
+    const T c1 = (T)0.30901699437494742410229341718282, c2 = (T)-0.80901699437494742410229341718282;
+    const T s1 = (T)-0.95105651629515357211643933337938, s2 = (T)-0.58778525229247312916870595463907;
+    C t1 = cadd(a[1], a[4]), d1 = csub(a[1], a[4]), t2 = cadd(a[2], a[3]), d2 = csub(a[2], a[3]);
+    C m1 = C{a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y};
+    C m2 = C{a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y};
+    C r1 = C{-(s1 * d1.y + s2 * d2.y), s1 * d1.x + s2 * d2.x};   // i*(s1 d1 + s2 d2)
+    C r2 = C{-(s2 * d1.y - s1 * d2.y), s2 * d1.x - s1 * d2.x};   // i*(s2 d1 - s1 d2)
+    a[0] = cadd(a[0], cadd(t1, t2));
+    a[1] = cadd(m1, r1); a[4] = csub(m1, r1); a[2] = cadd(m2, r2); a[3] = csub(m2, r2);
+  }
+}
+
+// generic odd-prime DFT via the root table (R <= 13): O(R^2)
+template <typename C>
+__device__ __forceinline__ void prime_dft(C* a, int R, const C* __restrict__ tw, long long N) {
+  C y[13];
+  const long long step = N / R;  // w_R = w_N^(N/R)
+  for (int q = 0; q < R; q++) {
+    C acc = a[0];
+    for (int r = 1; r < R; r++) acc = cadd(acc, cmul(a[r], tw[(long long)((r * q) % R) * step]));
+    y[q] = acc;
+  }
+  for (int q = 0; q < R; q++) a[q] = y[q];
+}
+
+template <typename C>
+__global__ void mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw,
+                                   real_of<C> scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = (int)p.N, TL = p.TL;
+  C* buf0 = reinterpret_cast<C*>(smem_raw);
+  C* buf1 = buf0 + (size_t)N * TL;
+  const long long nlines = p.O * p.I;
+  const long long l0 = (long long)blockIdx.x * TL;
+  const int nthreads = blockDim.x, tid = threadIdx.x;
+  // load: smem layout [line][n]
+  for (int idx = tid; idx < N * TL; idx += nthreads) {
+    int l, n;
+    if (p.line_fast) { l = idx % TL; n = idx / TL; } else { n = idx % N; l = idx / N; }
+    const long long line = l0 + l;
+    C v = C{0, 0};
+    if (line < nlines) {
+      const long long o = line / p.I, i = line % p.I;
+      v = in[o * p.N * p.I + (long long)n * p.I + i];
+      if (p.swap_in) v = cswap(v);
+    }
+    buf0[l * N + n] = v;
+  }
+  __syncthreads();
+  C* src = buf0;
+  C* dst = buf1;
+  int Ns = 1;
+  for (int s = 0; s < p.nstages; s++) {
+    const int R = p.radix[s];
+    const int nb = N / R;  // butterflies per line
+    for (int idx = tid; idx < nb * TL; idx += nthreads) {
+      const int l = idx / nb, j = idx % nb;
+      const int k = j % Ns;
+      C a[13];
+      const C* sp = src + l * N;
+      const long long tstep = (long long)(N / (Ns * R)) * k;  // w_{Ns R}^{r k} = w_N^{r k N/(Ns R)}
+      for (int r = 0; r < R; r++) {
+        C v = sp[j + r * nb];
+        if (r > 0 && k > 0) v = cmul(v, tw[(tstep * r) % N]);
+        a[r] = v;
+      }
+      switch (R) {
+        case 2: small_dft<2>(a); break;
+        case 3: small_dft<3>(a); break;
+        case 4: small_dft<4>(a); break;
+        case 5: small_dft<5>(a); break;
+        default: prime_dft(a, R, tw, p.N); break;
+      }
+      C* dp = dst + l * N + (j / Ns) * Ns * R + k;
+      for (int q = 0; q < R; q++) dp[q * Ns] = a[q];
+    }
+    __syncthreads();
+    C* t = src; src = dst; dst = t;
+    Ns *= R;
+  }
+  for (int idx = tid; idx < N * TL; idx += nthreads) {
+    int l, n;
+    if (p.line_fast) { l = idx % TL; n = idx / TL; } else { n = idx % N; l = idx / N; }
+    const long long line = l0 + l;
+    if (line < nlines) {
+      const long long o = line / p.I, i = line % p.I;
+      C v = src[l * N + n];
+      v.x *= scale; v.y *= scale;
+      if (p.swap_out) v = cswap(v);
+      out[o * p.N * p.I + (long long)n * p.I + i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static const size_t kMixedSmemCap = 160 * 1024;
+static const size_t kBluesteinWorkspaceCap = 512ull << 20;  // per buffer
+
+static bool factor_small(long long n, std::vector<int>* f) {
+  f->clear();
+  while (n % 4 == 0) { f->push_back(4); n /= 4; }
+  while (n % 2 == 0) { f->push_back(2); n /= 2; }
+  for (int pr : {3, 5, 7, 11, 13})
+    while (n % pr == 0) { f->push_back(pr); n /= pr; }
+  return n == 1;
+}
+
+template <typename T>
+static void fill_roots(std::vector<T>& v, long long N) {
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (long long m = 0; m < N; m++) {
+    long double a = two_pi * (long double)m / (long double)N;
+    v[2 * m] = (T)cosl(a);
+    v[2 * m + 1] = (T)(-sinl(a));
+  }
+}
+
+int plan_generic_axis(int is_double, long long O, long long N, long long I, GenericPass* gp, const Uploader& up) {
+  const size_t esz = is_double ? 16 : 8;
+  gp->O = O; gp->N = N; gp->I = I; gp->lines = O * I;
+  std::vector<int> f;
+  const bool smooth = factor_small(N, &f);
+  if (smooth && (size_t)N * esz * 2 <= kMixedSmemCap && f.size() <= 12) {
+    gp->bluestein = 0;
+    gp->nstages = (int)f.size();
+    // largest radices first: the stage with Ns == 1 has no twiddles
+    for (size_t i = 0; i < f.size(); i++) gp->radix[i] = f[f.size() - 1 - i];
+    int TL = (int)(kMixedSmemCap / ((size_t)N * esz * 2));
+    const int want = I > 1 ? 16 : 8;
+    if (TL > want) TL = want;
+    if (TL < 1) TL = 1;
+    if ((long long)TL > gp->lines) TL = (int)gp->lines;
+    gp->TL = TL;
+    gp->smem = (size_t)N * TL * esz * 2;
+    long long work = (N / 2) * TL;
+    gp->threads = work >= 512 ? 512 : work >= 256 ? 256 : work >= 128 ? 128 : 64;
+    if (is_double) { std::vector<double> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(double)); }
+    else { std::vector<float> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(float)); }
+    if (!gp->tw) return B200FFT_ALLOC_FAILED;
+    snprintf(gp->desc, sizeof gp->desc, "mixed-radix N=%lld stages=%d TL=%d threads=%d smem=%zu (O=%lld I=%lld)", N, gp->nstages,
+             gp->TL, gp->threads, gp->smem, O, I);
+    return 0;
+  }
+  // ---- Bluestein -------------------------------------------------------------------------
+  gp->bluestein = 1;
+  long long M = 1;
+  while (M < 2 * N - 1) M <<= 1;
+  gp->M = M;
+  long long chunk = (long long)(kBluesteinWorkspaceCap / ((size_t)M * esz));
+  if (chunk < 1) chunk = 1;
+  if (chunk > gp->lines) chunk = gp->lines;
+  gp->chunk_lines = chunk;
+  gp->workspace_bytes = 2 * (size_t)chunk * M * esz;
+  // chirp[n] = exp(-i pi n^2 / N), n^2 reduced mod 2N exactly
+  std::vector<double> hc(2 * (size_t)N), hb(2 * (size_t)M, 0.0);
+  const long double pi = 3.141592653589793238462643383279502884L;
+  for (long long n = 0; n < N; n++) {
+    long long r = (long long)(((unsigned __int128)n * n) % (unsigned long long)(2 * N));
+    long double a = pi * (long double)r / (long double)N;
+    long double c = cosl(a), s = sinl(a);
+    hc[2 * n] = (double)c; hc[2 * n + 1] = (double)(-s);
+    // b = conj(chirp), wrapped
+    hb[2 * n] = (double)c; hb[2 * n + 1] = (double)s;
+    if (n > 0) { hb[2 * (M - n)] = (double)c; hb[2 * (M - n) + 1] = (double)s; }
+  }
+  // filter = FFT_M(b) / M, computed once on the device in double with our own engine
+  b200fftHandle fp = nullptr;
+  int e = b200fftPlanMany1d(&fp, M, 1, B200FFT_Z2Z);
+  if (e) return e;
+  void *db = nullptr, *df = nullptr;
+  if (cudaMalloc(&db, (size_t)M * 16) != cudaSuccess || cudaMalloc(&df, (size_t)M * 16) != cudaSuccess) {
+    if (db) cudaFree(db);
+    b200fftDestroy(fp);
+    return B200FFT_ALLOC_FAILED;
+  }
+  cudaMemcpy(db, hb.data(), (size_t)M * 16, cudaMemcpyHostToDevice);
+  e = b200fftExecScaled(fp, db, df, B200FFT_FORWARD, 1.0 / (double)M, nullptr);
+  std::vector<double> hf(2 * (size_t)M);
+  cudaError_t ce = cudaMemcpy(hf.data(), df, (size_t)M * 16, cudaMemcpyDeviceToHost);
+  cudaFree(db); cudaFree(df);
+  b200fftDestroy(fp);
+  if (e || ce != cudaSuccess) return e ? e : B200FFT_EXEC_FAILED;
+  if (is_double) {
+    gp->chirp = up(hc.data(), hc.size() * sizeof(double));
+    gp->filt = up(hf.data(), hf.size() * sizeof(double));
+  } else {
+    std::vector<float> c32(hc.begin(), hc.end()), f32(hf.begin(), hf.end());
+    gp->chirp = up(c32.data(), c32.size() * sizeof(float));
+    gp->filt = up(f32.data(), f32.size() * sizeof(float));
+  }
+  if (!gp->chirp || !gp->filt) return B200FFT_ALLOC_FAILED;
+  e = b200fftPlanMany1d(&gp->sub, M, chunk, is_double ? B200FFT_Z2Z : B200FFT_C2C);
+  if (e) return e;
+  snprintf(gp->desc, sizeof gp->desc, "bluestein N=%lld M=%lld chunk=%lld lines (%d sub-passes x2 + 3 pointwise) (O=%lld I=%lld)", N, M,
+           chunk, b200fftNumPasses(gp->sub), O, I);
+  return 0;
+}
+
+void destroy_generic(GenericPass* gp) {
+  if (gp->sub) { b200fftDestroy(gp->sub); gp->sub = nullptr; }
+}
+
+template <typename C>
+static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst, void* workspace, int inverse, double scale,
+                                    cudaStream_t stream, long long* nl) {
+  using T = real_of<C>;
+  if (!gp.bluestein) {
+    MixedParams mp{};
+    mp.O = gp.O; mp.N = gp.N; mp.I = gp.I; mp.nstages = gp.nstages;
+    for (int i = 0; i < gp.nstages; i++) mp.radix[i] = gp.radix[i];
+    mp.TL = gp.TL; mp.line_fast = gp.I > 1;
+    mp.swap_in = mp.swap_out = 0;
+    // the caller folds first/last-pass information into `inverse`: see launch_generic
+    mp.swap_in = inverse & 1; mp.swap_out = (inverse >> 1) & 1;
+    const long long tiles = (gp.lines + gp.TL - 1) / gp.TL;
+    mixed_radix_kernel<C><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
+    *nl += 1;
+    return cudaGetLastError();
+  }
+  const long long M = gp.M, N = gp.N;
+  C* A = (C*)workspace;
+  C* B = A + gp.chunk_lines * M;
+  const int swap_in = inverse & 1, swap_out = (inverse >> 1) & 1;
+  for (long long l0 = 0; l0 < gp.lines; l0 += gp.chunk_lines) {
+    const long long nlc = (gp.lines - l0 < gp.chunk_lines) ? gp.lines - l0 : gp.chunk_lines;
+    const int thr = 256;
+    auto blocks = [&](long long total) { long long b = (total + thr - 1) / thr; return (unsigned)(b > 148 * 32 ? 148 * 32 : b); };
+    chirp_pack_kernel<C><<<blocks(nlc * M), thr, 0, stream>>>(src, A, (const C*)gp.chirp, N, gp.I, M, l0, nlc, swap_in);
+    int e = b200fftExec(gp.sub, A, B, B200FFT_FORWARD, stream);
+    if (e) return cudaErrorUnknown;
+    filt_mul_kernel<C><<<blocks(gp.chunk_lines * M), thr, 0, stream>>>(B, (const C*)gp.filt, M, gp.chunk_lines * M);
+    e = b200fftExec(gp.sub, B, A, B200FFT_INVERSE, stream);
+    if (e) return cudaErrorUnknown;
+    chirp_unpack_kernel<C><<<blocks(nlc * N), thr, 0, stream>>>(A, dst, (const C*)gp.chirp, N, gp.I, M, l0, nlc, swap_out, (T)scale);
+    *nl += 3;
+  }
+  return cudaGetLastError();
+}
+
+// `inverse` bit 0: swap re/im on load (first pass of an inverse plan); bit 1: swap on store (last pass)
+cudaError_t launch_generic(int is_double, const GenericPass& gp, const void* src, void* dst, void* workspace, int inverse,
+                           double scale, cudaStream_t stream, long long* nl) {
+  if (is_double) return launch_generic_t<double2>(gp, (const double2*)src, (double2*)dst, workspace, inverse, scale, stream, nl);
+  return launch_generic_t<float2>(gp, (const float2*)src, (float2*)dst, workspace, inverse, scale, stream, nl);
+}
+
+cudaError_t launch_copy_scale(int is_double, const void* src, void* dst, long long count, double scale, cudaStream_t stream,
+                              long long* nl) {
+  long long b = (count + 255) / 256;
+  unsigned blocks = (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+  if (is_double) copy_scale_kernel<double2><<<blocks, 256, 0, stream>>>((const double2*)src, (double2*)dst, count, scale);
+  else copy_scale_kernel<float2><<<blocks, 256, 0, stream>>>((const float2*)src, (float2*)dst, count, (float)scale);
+  *nl += 1;
+  return cudaGetLastError();
+}
+
+int generic_set_attrs() {
+  if (cudaFuncSetAttribute(mixed_radix_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
+    return B200FFT_INTERNAL_ERROR;
+  if (cudaFuncSetAttribute(mixed_radix_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
+    return B200FFT_INTERNAL_ERROR;
+  return 0;
+}
+
+}  // namespace b200fft

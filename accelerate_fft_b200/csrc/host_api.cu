@@ -1,0 +1,202 @@
+// Host-side mirror of the reference's operator interface for this path, above the C ABI.
+// The reference's host side is Haskell (FFT.hs, LLVM/PTX.hs, LLVM/PTX/Plans.hs); GHC is not in
+// this image, so the same logic is restated in C++ and exported with C linkage for the tests.
+// The Haskell shim that a maintainer would actually ship is in haskell/ (see INTEGRATION.md).
+//
+//   Mode / signOfMode            <- Mode.hs:15-26
+//   fft / fft1D / fft2D / fft3D  <- FFT.hs:63-173 (dispatch + Inverse scaling) and PTX.hs:52-70
+//   Plans / withPlan             <- PTX/Plans.hs:40-90 (one cache per entry point, keyed by
+//                                   (context, shape, type); creation under a lock, exec outside it)
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "generic.h"
+
+namespace {
+
+enum Mode { Forward = 0, Reverse = 1, Inverse = 2 };  // Mode.hs:15-19
+
+// PTX.hs:130-132 fftMode
+int fft_direction(int mode) { return mode == Forward ? B200FFT_FORWARD : B200FFT_INVERSE; }
+
+// PTX/Plans.hs:40-44: the reference keys on (context pointer, hash of (shape,type)); we key on the
+// full tuple so two shapes can never share a plan through a hash collision.
+using Key = std::tuple<void*, int, int64_t, int64_t, int64_t>;  // ctx, type, d, h, w
+
+struct Plans {
+  std::mutex lock;
+  std::map<Key, b200fftHandle> plans;
+  int (*create)(b200fftHandle*, int64_t, int64_t, int64_t, int);
+};
+
+int mk1d(b200fftHandle* h, int64_t, int64_t, int64_t n, int t) { return b200fftPlan1d(h, n, t, 1); }                   // PTX.hs:141
+int mk2d(b200fftHandle* h, int64_t, int64_t hh, int64_t w, int t) { return b200fftPlan2d(h, hh, w, t); }                // PTX.hs:148
+int mk3d(b200fftHandle* h, int64_t d, int64_t hh, int64_t w, int t) { return b200fftPlan3d(h, d, hh, w, t); }           // PTX.hs:155
+int mk2many(b200fftHandle* h, int64_t, int64_t hh, int64_t w, int t) { return b200fftPlanMany1d(h, w, hh, t); }         // PTX.hs:162
+int mk3many(b200fftHandle* h, int64_t d, int64_t hh, int64_t w, int t) { return b200fftPlanMany1d(h, w, d * hh, t); }   // PTX.hs:169
+
+// PTX.hs:137-170: five global caches
+Plans fft1D_plans{{}, {}, mk1d}, fft2D_plans{{}, {}, mk2d}, fft3D_plans{{}, {}, mk3d}, fft2DMany_plans{{}, {}, mk2many},
+    fft3DMany_plans{{}, {}, mk3many};
+Plans* all_caches[] = {&fft1D_plans, &fft2D_plans, &fft3D_plans, &fft2DMany_plans, &fft3DMany_plans};
+
+bool g_fused_inverse = false;
+
+// PTX/Plans.hs:66-86 withPlan: look up / create under the lock, return the handle, run outside it
+int with_plan(Plans& ps, int64_t d, int64_t h, int64_t w, int type, b200fftHandle* out) {
+  // The driver entry point is fetched through the runtime so the library carries no link-time
+  // dependency on libcuda.so (it must load, and report NO_DEVICE, on a box without a driver).
+  typedef CUresult (*ctx_get_t)(CUcontext*);
+  static ctx_get_t ctx_get = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &fn, cudaEnableDefault, &qr) != cudaSuccess) { cudaGetLastError(); fn = nullptr; }
+    return (ctx_get_t)fn;
+  }();
+  if (!ctx_get) return B200FFT_NO_DEVICE;
+  CUcontext ctx = nullptr;
+  if (ctx_get(&ctx) != CUDA_SUCCESS || ctx == nullptr) {
+    // runtime-API callers may not have touched the device yet: force the primary context
+    if (cudaFree(0) != cudaSuccess) { cudaGetLastError(); return B200FFT_NO_DEVICE; }
+    if (ctx_get(&ctx) != CUDA_SUCCESS || ctx == nullptr) return B200FFT_NO_DEVICE;
+  }
+  std::lock_guard<std::mutex> g(ps.lock);
+  Key key{(void*)ctx, type, d, h, w};
+  auto it = ps.plans.find(key);
+  if (it != ps.plans.end()) { *out = it->second; return 0; }
+  b200fftHandle hnd = nullptr;
+  int e = ps.create(&hnd, d, h, w, type);
+  if (e) return e;
+  ps.plans.emplace(key, hnd);
+  *out = hnd;
+  return 0;
+}
+
+template <typename C, typename T>
+__global__ void scale_kernel(C* a, long long n, T s) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    C v = a[i];
+    v.x = v.x / s; v.y = v.y / s;   // A.map (/scale), FFT.hs:83
+    a[i] = v;
+  }
+}
+
+// fft' (PTX.hs:77-106) + the Inverse post-scale of FFT.hs
+int run(Plans& ps, int mode, int64_t d, int64_t h, int64_t w, int type, double scale, const void* in, void* out,
+        b200fftStream stream) {
+  if (mode < Forward || mode > Inverse) return B200FFT_INVALID_VALUE;
+  if (type != B200FFT_C2C && type != B200FFT_Z2Z) return B200FFT_INVALID_TYPE;
+  b200fftHandle hnd = nullptr;
+  if (int e = with_plan(ps, d, h, w, type, &hnd)) return e;
+  if (mode == Inverse && g_fused_inverse) return b200fftExecScaled(hnd, in, out, fft_direction(mode), 1.0 / scale, stream);
+  if (int e = b200fftExec(hnd, in, out, fft_direction(mode), stream)) return e;
+  if (mode == Inverse) {  // case mode of Inverse -> A.map (/scale) (go arr)
+    const long long n = (long long)d * h * w;
+    long long b = (n + 255) / 256;
+    unsigned blocks = (unsigned)(b > 148 * 16 ? 148 * 16 : b);
+    if (type == B200FFT_C2C) scale_kernel<float2, float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float2*)out, n, (float)scale);
+    else scale_kernel<double2, double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double2*)out, n, scale);
+    if (cudaGetLastError() != cudaSuccess) return B200FFT_EXEC_FAILED;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// FFT.hs:63-84 fft: innermost axis; PTX.hs:52-61 rank dispatch (DIM1 -> fft1D plans, DIM2/DIM3 -> many plans).
+// Ranks above 3 are accepted by collapsing the outer extents into the batch; the reference's
+// PTX.fft raises internalError there (PTX.hs:61) and falls back to the pure path.
+int accfft_fft(int mode, int rank, const int64_t* shape, int type, const void* in, void* out, b200fftStream stream) {
+  if (rank < 1 || !shape) return B200FFT_INVALID_VALUE;
+  for (int i = 0; i < rank; i++) if (shape[i] < 0) return B200FFT_INVALID_SIZE;
+  int64_t w = shape[rank - 1];
+  int64_t outer = 1;
+  for (int i = 0; i < rank - 1; i++) outer *= shape[i];
+  if (w == 0 || outer == 0) return 0;  // empty array: nothing to do
+  const double scale = (double)w;      // FFT.hs:69
+  if (rank == 1) return run(fft1D_plans, mode, 1, 1, w, type, scale, in, out, stream);
+  if (rank == 2) return run(fft2DMany_plans, mode, 1, shape[0], w, type, scale, in, out, stream);
+  if (rank == 3) return run(fft3DMany_plans, mode, shape[0], shape[1], w, type, scale, in, out, stream);
+  // scale is the innermost length only; the plan key collapses the outer extents
+  b200fftHandle hnd = nullptr;
+  (void)hnd;
+  return run(fft3DMany_plans, mode, 1, outer, w, type, scale, in, out, stream);
+}
+
+int accfft_fft1D(int mode, int64_t n, int type, const void* in, void* out, b200fftStream stream) {
+  if (n < 0) return B200FFT_INVALID_SIZE;
+  if (n == 0) return 0;
+  return run(fft1D_plans, mode, 1, 1, n, type, (double)n, in, out, stream);  // FFT.hs:98
+}
+
+int accfft_fft2D(int mode, int64_t h, int64_t w, int type, const void* in, void* out, b200fftStream stream) {
+  if (h < 0 || w < 0) return B200FFT_INVALID_SIZE;
+  if (h == 0 || w == 0) return 0;
+  // scale by the whole size, FFT.hs:125; run() takes it separately from the plan key
+  b200fftHandle hnd = nullptr;
+  (void)hnd;
+  return run(fft2D_plans, mode, 1, h, w, type, (double)h * (double)w, in, out, stream);
+}
+
+int accfft_fft3D(int mode, int64_t d, int64_t h, int64_t w, int type, const void* in, void* out, b200fftStream stream) {
+  if (d < 0 || h < 0 || w < 0) return B200FFT_INVALID_SIZE;
+  if (d == 0 || h == 0 || w == 0) return 0;
+  return run(fft3D_plans, mode, d, h, w, type, (double)d * (double)h * (double)w, in, out, stream);  // FFT.hs:155
+}
+
+int accfft_run_host(int kind, int mode, int rank, const int64_t* shape, int type, const void* h_in, void* h_out) {
+  if (rank < 1 || rank > 8 || !shape) return B200FFT_INVALID_VALUE;
+  if ((kind == 1 && rank != 1) || (kind == 2 && rank != 2) || (kind == 3 && rank != 3)) return B200FFT_INVALID_VALUE;
+  long long n = 1;
+  for (int i = 0; i < rank; i++) n *= shape[i];
+  if (n == 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return B200FFT_NO_DEVICE; }
+  const size_t bytes = (size_t)n * (type == B200FFT_Z2Z ? 16 : 8);
+  void *d_in = nullptr, *d_out = nullptr;
+  if (cudaMalloc(&d_in, bytes) != cudaSuccess) { cudaGetLastError(); return B200FFT_ALLOC_FAILED; }
+  if (cudaMalloc(&d_out, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(d_in); return B200FFT_ALLOC_FAILED; }
+  int e = 0;
+  if (cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) e = B200FFT_EXEC_FAILED;
+  if (!e) {
+    switch (kind) {
+      case 0: e = accfft_fft(mode, rank, shape, type, d_in, d_out, nullptr); break;
+      case 1: e = accfft_fft1D(mode, shape[0], type, d_in, d_out, nullptr); break;
+      case 2: e = accfft_fft2D(mode, shape[0], shape[1], type, d_in, d_out, nullptr); break;
+      case 3: e = accfft_fft3D(mode, shape[0], shape[1], shape[2], type, d_in, d_out, nullptr); break;
+      default: e = B200FFT_INVALID_VALUE;
+    }
+  }
+  if (!e && cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, 0) != cudaSuccess) e = B200FFT_EXEC_FAILED;
+  if (cudaStreamSynchronize(0) != cudaSuccess && !e) e = B200FFT_EXEC_FAILED;
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e) cudaGetLastError();
+  return e;
+}
+
+void accfft_set_fused_inverse(int on) { g_fused_inverse = on != 0; }
+
+int accfft_plan_cache_size(void) {
+  int n = 0;
+  for (Plans* p : all_caches) { std::lock_guard<std::mutex> g(p->lock); n += (int)p->plans.size(); }
+  return n;
+}
+
+void accfft_plan_cache_clear(void) {
+  for (Plans* p : all_caches) {
+    std::lock_guard<std::mutex> g(p->lock);
+    for (auto& kv : p->plans) b200fftDestroy(kv.second);
+    p->plans.clear();
+  }
+}
+
+}  // extern "C"

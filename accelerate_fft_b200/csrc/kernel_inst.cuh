@@ -1,0 +1,27 @@
+// Helper included by the kernels_*.cu instantiation units.
+#pragma once
+#include "fft_kernel.cuh"
+#include "registry.h"
+
+namespace b200fft {
+
+template <class K, bool LLF, bool SLF, bool TW4>
+KernelEntry make_entry() {
+  KernelEntry e{};
+  e.is_double = sizeof(typename K::real) == 8;
+  e.N = K::N; e.E = K::E; e.TL = K::TL; e.threads = K::THREADS;
+  e.flavor = (LLF && SLF) ? FL_COL : (!LLF && SLF) ? FL_TRANS : FL_ROW;
+  e.tw4 = TW4;
+  e.smem = K::template smem_bytes<(LLF && SLF)>();
+  e.S = K::S;
+  for (int i = 0; i < 4; i++) e.rad[i] = K::rad[i];
+  e.tw_len = K::TW_LEN;
+  e.func = reinterpret_cast<const void*>(&fft_lines_kernel<K, LLF, SLF, TW4>);
+  return e;
+}
+
+#define REG_ROW(...)   add(make_entry<Cfg<__VA_ARGS__>, false, false, false>())
+#define REG_COL(...)   add(make_entry<Cfg<__VA_ARGS__>, true, true, false>()); add(make_entry<Cfg<__VA_ARGS__>, true, true, true>())
+#define REG_TRANS(...) add(make_entry<Cfg<__VA_ARGS__>, false, true, false>())
+
+}  // namespace b200fft

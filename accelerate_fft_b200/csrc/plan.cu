@@ -1,0 +1,560 @@
+// Planner + executor + C ABI of libb200fft (see include/b200fft.h).
+//
+// A plan is an immutable list of passes; each pass is one launch of a line kernel (fft_kernel.cuh,
+// generic_kernel.cu) = one HBM read + one HBM write of the whole array.  Exec enqueues the passes on
+// the caller's stream; scratch is stream-ordered (cudaMallocAsync) so concurrent execs of one plan
+// on different streams do not share state (cf. PTX/Plans.hs:86 -- exec runs outside the cache lock).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "generic.h"
+#include "registry.h"
+#include "fft_kernel.cuh"
+
+namespace b200fft {
+
+// ------------------------------------------------------------------------------------------
+// registry
+// ------------------------------------------------------------------------------------------
+static std::vector<KernelEntry>& reg() {
+  static std::vector<KernelEntry> r;
+  return r;
+}
+static void add_entry(const KernelEntry& e) { reg().push_back(e); }
+static std::once_flag g_reg_once;
+static void ensure_registry() {
+  std::call_once(g_reg_once, [] {
+    register_f32_small(add_entry);
+    register_f32_large(add_entry);
+    register_f32_col(add_entry);
+    register_f64_small(add_entry);
+    register_f64_large(add_entry);
+    register_f64_col(add_entry);
+  });
+}
+
+const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int prefer_tl) {
+  ensure_registry();
+  const KernelEntry* best = nullptr;
+  for (const auto& e : reg()) {
+    if (e.is_double != is_double || e.N != N || e.flavor != flavor || e.tw4 != tw4) continue;
+    if (!best) best = &e;
+    else if (prefer_tl > 0 && std::abs(e.TL - prefer_tl) < std::abs(best->TL - prefer_tl)) best = &e;
+  }
+  return best;
+}
+int list_kernels(const KernelEntry** out, int max) {
+  ensure_registry();
+  int n = 0;
+  for (const auto& e : reg()) { if (n < max) out[n] = &e; n++; }
+  return n;
+}
+
+static std::atomic<long long> g_launches{0};
+
+// ------------------------------------------------------------------------------------------
+// plan representation
+// ------------------------------------------------------------------------------------------
+enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
+
+enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3 };
+
+struct Pass {
+  int kind = PK_LINES;
+  const KernelEntry* k = nullptr;  // PK_LINES
+  Geom g{};
+  GenericPass gp{};                // PK_GENERIC / PK_BLUESTEIN
+  bool inplace_ok = false;         // reads and writes the same positions tile by tile
+  int src = BUF_IN, dst = BUF_OUT;
+  void* tws = nullptr;             // device: stage twiddles
+  void* tw_lo = nullptr;           // device: four-step twiddle tables
+  void* tw_hi = nullptr;
+  long long ntiles = 0;
+  std::string desc;
+};
+
+}  // namespace b200fft
+
+using namespace b200fft;
+
+struct b200fft_plan_s {
+  unsigned magic = 0xB200FF7u;
+  int is_double = 0;
+  int rank = 0;
+  long long dims[3] = {1, 1, 1};
+  long long batch = 1;
+  long long total = 0;  // complex elements in / out
+  std::vector<Pass> passes;
+  std::vector<void*> dev_allocs;
+  size_t scratch_bytes = 0;   // main scratch (same size as the array) if any pass uses BUF_SCRATCH
+  size_t extra_bytes = 0;     // bluestein workspace
+};
+
+namespace b200fft {
+
+static size_t esize(const b200fft_plan_s* p) { return p->is_double ? 16 : 8; }
+
+template <typename T>
+static void* upload(b200fft_plan_s* p, const std::vector<T>& h) {
+  void* d = nullptr;
+  if (h.empty()) return nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  p->dev_allocs.push_back(d);
+  return d;
+}
+
+// exp(-2 pi i num/den) in long double with the argument reduced exactly
+static void unit_root(long long num, long long den, long double* re, long double* im) {
+  num %= den;
+  if (num < 0) num += den;
+  // octant reduction for accuracy
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  long double a = two_pi * (long double)num / (long double)den;
+  *re = cosl(a);
+  *im = -sinl(a);
+}
+
+template <typename T>
+static void fill_root_table(std::vector<T>& v, size_t off, long long num, long long den) {
+  long double re, im;
+  unit_root(num, den, &re, &im);
+  v[2 * off] = (T)re;
+  v[2 * off + 1] = (T)im;
+}
+
+// stage twiddles of a line kernel: stage s>=1, entry [(r-1)*Ns + k] = w_{Ns*R}^{r k}
+static void* make_stage_twiddles(b200fft_plan_s* p, const KernelEntry* k) {
+  if (k->tw_len == 0) return nullptr;
+  auto build = [&](auto tag) -> void* {
+    using T = decltype(tag);
+    std::vector<T> h(2 * (size_t)k->tw_len);
+    size_t off = 0;
+    int Ns = k->rad[0];
+    for (int s = 1; s < k->S; s++) {
+      int R = k->rad[s];
+      for (int r = 1; r < R; r++)
+        for (int kk = 0; kk < Ns; kk++) fill_root_table(h, off + (size_t)(r - 1) * Ns + kk, (long long)r * kk, (long long)Ns * R);
+      off += (size_t)(R - 1) * Ns;
+      Ns *= R;
+    }
+    return upload(p, h);
+  };
+  return p->is_double ? build(double{}) : build(float{});
+}
+
+// four-step twiddle w_L^x split as lo[x & (2^lb - 1)] * hi[x >> lb]
+static void make_fourstep_tables(b200fft_plan_s* p, long long L, int* lo_bits, void** lo, void** hi) {
+  int lg = 0;
+  while ((1LL << lg) < L) lg++;
+  int lb = (lg + 1) / 2;
+  *lo_bits = lb;
+  long long nlo = 1LL << lb, nhi = (L + nlo - 1) / nlo;
+  auto build = [&](auto tag) {
+    using T = decltype(tag);
+    std::vector<T> a(2 * (size_t)nlo), b(2 * (size_t)nhi);
+    for (long long i = 0; i < nlo; i++) fill_root_table(a, (size_t)i, i, L);
+    for (long long i = 0; i < nhi; i++) fill_root_table(b, (size_t)i, i << lb, L);
+    *lo = upload(p, a);
+    *hi = upload(p, b);
+  };
+  if (p->is_double) build(double{}); else build(float{});
+}
+
+static bool is_pow2(long long n) { return n > 0 && (n & (n - 1)) == 0; }
+static int ilog2(long long n) { int l = 0; while ((1LL << l) < n) l++; return l; }
+
+struct Builder {
+  b200fft_plan_s* p;
+  int err = 0;
+
+  Pass& push(Pass ps) { p->passes.push_back(std::move(ps)); return p->passes.back(); }
+
+  // ---- one launch of a pow2 line kernel --------------------------------------------------
+  // array viewed as [nb][no][N-axis...]; see Geom.  Returns false if no kernel exists.
+  bool lines_pass(int N, int flavor, bool tw4, Geom g, long long twL, bool inplace_ok, int prefer_tl, const char* what) {
+    const KernelEntry* k = find_kernel(p->is_double, N, flavor, tw4 ? 1 : 0, prefer_tl);
+    if (!k) return false;
+    Pass ps;
+    ps.kind = PK_LINES;
+    ps.k = k;
+    g.ntl = (g.nl + k->TL - 1) / k->TL;
+    ps.g = g;
+    ps.inplace_ok = inplace_ok;
+    ps.tws = make_stage_twiddles(p, k);
+    if (tw4) make_fourstep_tables(p, twL, &ps.g.tw_lo_bits, &ps.tw_lo, &ps.tw_hi);
+    ps.ntiles = (long long)g.nb * g.no * ps.g.ntl;
+    if (ps.ntiles >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return false; }
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: lines N=%d E=%d TL=%d %s%s radix=%dx%dx%dx%d threads=%d smem=%zu tiles=%lld", what, k->N,
+             k->E, k->TL, flavor == FL_ROW ? "row" : flavor == FL_COL ? "col" : "trans", tw4 ? "+tw" : "", k->rad[0], k->rad[1],
+             k->rad[2], k->rad[3], k->threads, k->smem, ps.ntiles);
+    ps.desc = buf;
+    push(ps);
+    return true;
+  }
+
+  int max_col_n() const { return 2048; }   // longest strided axis done in one pass (>= 64 B runs)
+  int max_row_n() const { return p->is_double ? 8192 : 16384; }  // largest N with a row kernel
+
+  // ---- transform along one axis of an array viewed as [O][N][I] (I = element stride of the axis)
+  void axis(long long O, long long N, long long I) {
+    if (err || N == 1) return;
+    if (O >= (1LL << 31) || I >= (1LL << 31) || N >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
+    if (!is_pow2(N)) { generic_axis(O, N, I); return; }
+    if (I == 1) {
+      if (N <= max_row_n()) {
+        Geom g{};
+        g.nb = 1; g.no = 1; g.nl = (int)O;
+        g.ils = N; g.ins = 1; g.ols = N; g.ons = 1;
+        g.tw_div = 1;
+        if (!lines_pass((int)N, FL_ROW, false, g, 0, true, 0, "rows")) err = B200FFT_INTERNAL_ERROR;
+        return;
+      }
+      fourstep_contig(O, N);
+      return;
+    }
+    if (N <= max_col_n()) {
+      // prefer a tile whose contiguous run is >= 128 B but keep the CTA's shared memory moderate
+      Geom g{};
+      g.nb = 1; g.no = (int)O; g.nl = (int)I;
+      g.ios = N * I; g.ils = 1; g.ins = I;
+      g.oos = N * I; g.ols = 1; g.ons = I;
+      g.tw_div = 1;
+      if (!lines_pass((int)N, FL_COL, false, g, 0, true, 0, "cols")) err = B200FFT_INTERNAL_ERROR;
+      return;
+    }
+    fourstep_strided(O, N, I);
+  }
+
+  // choose N1*N2 = N (both pow2) with N1, N2 <= lim, as balanced as possible
+  static bool split2(long long N, long long lim, long long* n1, long long* n2) {
+    int lg = ilog2(N);
+    int a = lg / 2, b = lg - a;
+    if ((1LL << b) > lim) return false;
+    *n1 = 1LL << a; *n2 = 1LL << b;
+    return true;
+  }
+
+  // four-step along a strided axis: [O][N][I], N = N1*N2, n = n1*N2 + n2, k = k1 + N1*k2
+  void fourstep_strided(long long O, long long N, long long I) {
+    long long N1, N2;
+    // small sub-lengths keep the [N][TL] tiles small; cap at 1024 so TL stays >= 8
+    if (!split2(N, 1024, &N1, &N2)) { err = B200FFT_NOT_SUPPORTED; return; }
+    if (N2 * I >= (1LL << 31) || O * N1 >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
+    {  // pass A: FFT over n1, lines = (n2,i), twiddle w_N^(k1*n2), same positions
+      Geom g{};
+      g.nb = 1; g.no = (int)O; g.nl = (int)(N2 * I);
+      g.ios = N * I; g.ils = 1; g.ins = N2 * I;
+      g.oos = N * I; g.ols = 1; g.ons = N2 * I;
+      g.tw_div = (int)I;
+      if (!lines_pass((int)N1, FL_COL, true, g, N, true, 0, "4step-A")) { err = B200FFT_INTERNAL_ERROR; return; }
+    }
+    {  // pass B: FFT over n2 for each (o,k1); out row index k1 + N1*k2
+      Geom g{};
+      g.nb = (int)O; g.no = (int)N1; g.nl = (int)I;
+      g.ibs = N * I; g.ios = N2 * I; g.ils = 1; g.ins = I;
+      g.obs = N * I; g.oos = I; g.ols = 1; g.ons = N1 * I;
+      g.tw_div = 1;
+      if (!lines_pass((int)N2, FL_COL, false, g, 0, false, 0, "4step-B")) { err = B200FFT_INTERNAL_ERROR; return; }
+    }
+  }
+
+  // four-step for contiguous lines: [O][N], 2 or 3 factors
+  void fourstep_contig(long long O, long long N) {
+    const long long lim = 1024;  // column / transposing tiles of <= 1024 points keep >= 64 B contiguous runs
+    int lg = ilog2(N);
+    if (N <= lim * lim) {
+      long long N1 = 1LL << (lg / 2), N2 = N / N1;
+      {  // A: FFT over n1 (stride N2), lines n2, twiddle w_N^(k1*n2)
+        Geom g{};
+        g.nb = 1; g.no = (int)O; g.nl = (int)N2;
+        g.ios = N; g.ils = 1; g.ins = N2;
+        g.oos = N; g.ols = 1; g.ons = N2;
+        g.tw_div = 1;
+        if (!lines_pass((int)N1, FL_COL, true, g, N, true, 0, "4step-A")) { err = B200FFT_INTERNAL_ERROR; return; }
+      }
+      {  // B: rows n2 for each k1, transposed store X[k1 + N1*k2]; lines = k1
+        Geom g{};
+        g.nb = (int)O; g.no = 1; g.nl = (int)N1;
+        g.ibs = N; g.ils = N2; g.ins = 1;
+        g.obs = N; g.ols = 1; g.ons = N1;
+        g.tw_div = 1;
+        if (!lines_pass((int)N2, FL_TRANS, false, g, 0, false, 0, "4step-B")) { err = B200FFT_INTERNAL_ERROR; return; }
+      }
+      return;
+    }
+    if (N > lim * lim * lim) { err = B200FFT_NOT_SUPPORTED; return; }
+    // three factors: n = n1*M + n2*N3 + n3 (M = N2*N3), k = k1 + N1*k2 + N1*N2*k3
+    int a = lg / 3, b = (lg - a) / 2, c = lg - a - b;
+    long long N1 = 1LL << c, N2 = 1LL << b, N3 = 1LL << a;  // largest first: column tiles are cheapest to keep big
+    long long M = N2 * N3;
+    if (O * N1 >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
+    {  // A: FFT over n1 (stride M), lines m < M, twiddle w_N^(k1*m)
+      Geom g{};
+      g.nb = 1; g.no = (int)O; g.nl = (int)M;
+      g.ios = N; g.ils = 1; g.ins = M;
+      g.oos = N; g.ols = 1; g.ons = M;
+      g.tw_div = 1;
+      if (!lines_pass((int)N1, FL_COL, true, g, N, true, 0, "6step-A")) { err = B200FFT_INTERNAL_ERROR; return; }
+    }
+    {  // B: for each (o,k1): FFT over n2 (stride N3), lines n3, twiddle w_M^(k2*n3)
+      Geom g{};
+      g.nb = 1; g.no = (int)(O * N1); g.nl = (int)N3;
+      g.ios = M; g.ils = 1; g.ins = N3;
+      g.oos = M; g.ols = 1; g.ons = N3;
+      g.tw_div = 1;
+      if (!lines_pass((int)N2, FL_COL, true, g, M, true, 0, "6step-B")) { err = B200FFT_INTERNAL_ERROR; return; }
+    }
+    {  // C: rows n3 for each (k1,k2); lines = k1; X[k1 + N1*k2 + N1*N2*k3]
+      Geom g{};
+      g.nb = (int)O; g.no = (int)N2; g.nl = (int)N1;
+      g.ibs = N; g.ios = N3; g.ils = M; g.ins = 1;
+      g.obs = N; g.oos = N1; g.ols = 1; g.ons = N1 * N2;
+      g.tw_div = 1;
+      if (!lines_pass((int)N3, FL_TRANS, false, g, 0, false, 0, "6step-C")) { err = B200FFT_INTERNAL_ERROR; return; }
+    }
+  }
+
+  // ---- arbitrary (non power-of-two) axis lengths: generic_kernel.cu -----------------------
+  void generic_axis(long long O, long long N, long long I) {
+    Pass ps;
+    int e = plan_generic_axis(p->is_double, O, N, I, &ps.gp, [&](const void* h, size_t bytes) -> void* {
+      void* d = nullptr;
+      if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+      cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice);
+      p->dev_allocs.push_back(d);
+      return d;
+    });
+    if (e) { err = e; return; }
+    ps.kind = ps.gp.bluestein ? PK_BLUESTEIN : PK_GENERIC;
+    ps.inplace_ok = true;
+    ps.desc = ps.gp.desc;
+    if (ps.gp.workspace_bytes > p->extra_bytes) p->extra_bytes = ps.gp.workspace_bytes;
+    push(ps);
+  }
+
+  // ---- assign buffers: the input is never written, the last moving pass lands in `out` ----
+  void route() {
+    auto& P = p->passes;
+    if (P.empty()) {  // all extents 1: the transform is the identity
+      Pass ps; ps.kind = PK_COPY; ps.desc = "copy (identity transform)";
+      P.push_back(ps);
+    }
+    int q = 0;
+    for (int i = (int)P.size() - 1; i > 0; i--)
+      if (!P[i].inplace_ok) { q = i; break; }
+    // passes after q run in place on out; walk backwards alternating out/scratch at moving passes
+    int cur = BUF_OUT;
+    for (int i = (int)P.size() - 1; i >= 0; i--) {
+      P[i].dst = cur;
+      if (i == 0) { P[i].src = BUF_IN; break; }
+      if (i > q || P[i].inplace_ok) { P[i].src = cur; }
+      else { cur = (cur == BUF_OUT) ? BUF_SCRATCH : BUF_OUT; P[i].src = cur; }
+    }
+    bool uses_scratch = false;
+    for (auto& ps : P) uses_scratch |= (ps.src == BUF_SCRATCH || ps.dst == BUF_SCRATCH);
+    p->scratch_bytes = uses_scratch ? (size_t)p->total * esize(p) : 0;
+  }
+};
+
+static int set_func_attrs(const b200fft_plan_s* p) {
+  for (const auto& ps : p->passes) {
+    if (ps.kind == PK_LINES && ps.k->smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess)
+        return B200FFT_INTERNAL_ERROR;
+    }
+  }
+  return generic_set_attrs();
+}
+
+static int finish_plan(b200fft_plan_s* p, Builder& b, b200fftHandle* out) {
+  if (!b.err) b.route();
+  if (!b.err) b.err = set_func_attrs(p);
+  if (b.err) {
+    for (auto& ps : p->passes) destroy_generic(&ps.gp);
+    for (void* d : p->dev_allocs) cudaFree(d);
+    int e = b.err;
+    delete p;
+    cudaGetLastError();
+    return e;
+  }
+  *out = p;
+  return B200FFT_SUCCESS;
+}
+
+static int check_type(int type, int* is_double) {
+  if (type == B200FFT_C2C) { *is_double = 0; return 0; }
+  if (type == B200FFT_Z2Z) { *is_double = 1; return 0; }
+  return B200FFT_INVALID_TYPE;
+}
+
+static int have_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return B200FFT_NO_DEVICE; }
+  return 0;
+}
+
+}  // namespace b200fft
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200fftPlanMany1d(b200fftHandle* plan, int64_t n, int64_t batch, int type) {
+  if (!plan) return B200FFT_INVALID_VALUE;
+  int dbl;
+  if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
+  if (n < 1 || batch < 1) return B200FFT_INVALID_SIZE;
+  if (int e = have_device()) return e;
+  auto* p = new b200fft_plan_s;
+  p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = batch; p->total = n * batch;
+  Builder b{p};
+  b.axis(batch, n, 1);
+  return finish_plan(p, b, plan);
+}
+
+int b200fftPlan1d(b200fftHandle* plan, int64_t n, int type, int64_t batch) { return b200fftPlanMany1d(plan, n, batch, type); }
+
+int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type) {
+  if (!plan) return B200FFT_INVALID_VALUE;
+  int dbl;
+  if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
+  if (h < 1 || w < 1) return B200FFT_INVALID_SIZE;
+  if (int e = have_device()) return e;
+  auto* p = new b200fft_plan_s;
+  p->is_double = dbl; p->rank = 2; p->dims[0] = h; p->dims[1] = w; p->total = h * w;
+  Builder b{p};
+  b.axis(h, w, 1);   // rows
+  b.axis(1, h, w);   // columns
+  return finish_plan(p, b, plan);
+}
+
+int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type) {
+  if (!plan) return B200FFT_INVALID_VALUE;
+  int dbl;
+  if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
+  if (d < 1 || h < 1 || w < 1) return B200FFT_INVALID_SIZE;
+  if (int e = have_device()) return e;
+  auto* p = new b200fft_plan_s;
+  p->is_double = dbl; p->rank = 3; p->dims[0] = d; p->dims[1] = h; p->dims[2] = w; p->total = d * h * w;
+  Builder b{p};
+  b.axis(d * h, w, 1);   // x
+  b.axis(d, h, w);       // y
+  b.axis(1, d, h * w);   // z
+  return finish_plan(p, b, plan);
+}
+
+int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
+  if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
+  if (!in || !out || in == out) return B200FFT_INVALID_VALUE;
+  if (direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) return B200FFT_INVALID_VALUE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  void* scratch = nullptr;
+  void* extra = nullptr;
+  if (p->scratch_bytes && cudaMallocAsync(&scratch, p->scratch_bytes, stream) != cudaSuccess) { cudaGetLastError(); return B200FFT_ALLOC_FAILED; }
+  if (p->extra_bytes && cudaMallocAsync(&extra, p->extra_bytes, stream) != cudaSuccess) {
+    cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return B200FFT_ALLOC_FAILED;
+  }
+  const int inverse = direction == B200FFT_INVERSE;
+  int status = B200FFT_SUCCESS;
+  const size_t np = p->passes.size();
+  for (size_t i = 0; i < np && status == B200FFT_SUCCESS; i++) {
+    const Pass& ps = p->passes[i];
+    const void* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : scratch;
+    void* dst = ps.dst == BUF_OUT ? out : scratch;
+    const bool first = i == 0, last = i + 1 == np;
+    const double sc = last ? scale : 1.0;
+    cudaError_t ce = cudaSuccess;
+    if (ps.kind == PK_LINES) {
+      Geom g = ps.g;
+      g.swap_in = inverse && first;
+      g.swap_out = inverse && last;
+      float scf = (float)sc;
+      double scd = sc;
+      void* args[] = {&g, (void*)&src, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                      p->is_double ? (void*)&scd : (void*)&scf};
+      ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (ps.kind == PK_COPY) {
+      long long nl = 0;
+      ce = launch_copy_scale(p->is_double, src, dst, p->total, sc, stream, &nl);
+      g_launches.fetch_add(nl, std::memory_order_relaxed);
+    } else {
+      long long nl = 0;
+      ce = launch_generic(p->is_double, ps.gp, src, dst, extra, (inverse && first ? 1 : 0) | (inverse && last ? 2 : 0), sc, stream, &nl);
+      g_launches.fetch_add(nl, std::memory_order_relaxed);
+    }
+    if (ce != cudaSuccess) status = B200FFT_EXEC_FAILED;
+  }
+  if (scratch) cudaFreeAsync(scratch, stream);
+  if (extra) cudaFreeAsync(extra, stream);
+  if (status != B200FFT_SUCCESS) cudaGetLastError();
+  return status;
+}
+
+int b200fftExec(b200fftHandle plan, const void* in, void* out, int direction, b200fftStream stream) {
+  return b200fftExecScaled(plan, in, out, direction, 1.0, stream);
+}
+
+int b200fftDestroy(b200fftHandle p) {
+  if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
+  p->magic = 0;
+  for (auto& ps : p->passes) destroy_generic(&ps.gp);
+  // cudaFree is legal from any thread; if the owning context is already gone the error is benign
+  for (void* d : p->dev_allocs) cudaFree(d);
+  cudaGetLastError();
+  delete p;
+  return B200FFT_SUCCESS;
+}
+
+const char* b200fftErrorString(int s) {
+  switch (s) {
+    case B200FFT_SUCCESS: return "B200FFT_SUCCESS";
+    case B200FFT_INVALID_PLAN: return "B200FFT_INVALID_PLAN";
+    case B200FFT_ALLOC_FAILED: return "B200FFT_ALLOC_FAILED";
+    case B200FFT_INVALID_TYPE: return "B200FFT_INVALID_TYPE";
+    case B200FFT_INVALID_VALUE: return "B200FFT_INVALID_VALUE";
+    case B200FFT_INTERNAL_ERROR: return "B200FFT_INTERNAL_ERROR";
+    case B200FFT_EXEC_FAILED: return "B200FFT_EXEC_FAILED";
+    case B200FFT_INVALID_SIZE: return "B200FFT_INVALID_SIZE";
+    case B200FFT_NO_DEVICE: return "B200FFT_NO_DEVICE (no CUDA device/context: there is no CPU fallback)";
+    case B200FFT_NOT_SUPPORTED: return "B200FFT_NOT_SUPPORTED";
+    default: return "B200FFT_UNKNOWN_ERROR";
+  }
+}
+
+size_t b200fftScratchBytes(b200fftHandle p) { return p ? p->scratch_bytes + p->extra_bytes : 0; }
+int b200fftNumPasses(b200fftHandle p) { return p ? (int)p->passes.size() : 0; }
+int64_t b200fftKernelLaunches(void) { return g_launches.load(); }
+
+int b200fftDescribe(b200fftHandle p, char* buf, int buflen) {
+  if (!p || !buf || buflen <= 0) return 0;
+  std::string s;
+  static const char* bn[] = {"in", "out", "scratch"};
+  for (const auto& ps : p->passes) {
+    s += ps.desc;
+    s += " [";
+    s += bn[ps.src];
+    s += "->";
+    s += bn[ps.dst];
+    s += "]\n";
+  }
+  int n = (int)s.size() < buflen - 1 ? (int)s.size() : buflen - 1;
+  memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return n;
+}
+
+}  // extern "C"

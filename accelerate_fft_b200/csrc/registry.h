@@ -1,0 +1,34 @@
+// Kernel registry: every instantiated line kernel describes itself here so the planner
+// (plan.cu) can pick kernels by (type, N, flavour) without knowing template parameters.
+#pragma once
+#include <cstddef>
+
+namespace b200fft {
+
+enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2 };
+
+struct KernelEntry {
+  int is_double;
+  int N, E, TL, threads;
+  int flavor;      // FL_ROW: rows in / rows out; FL_COL: line-fastest both; FL_TRANS: rows in / line-fastest out
+  int tw4;         // multiplies by the four-step twiddle at the store
+  size_t smem;
+  int S, rad[4];
+  int tw_len;      // stage twiddle table length (complex elements)
+  const void* func;
+};
+
+template <class K, bool LLF, bool SLF, bool TW4> KernelEntry make_entry();
+
+const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int prefer_tl);
+int list_kernels(const KernelEntry** out, int max);
+
+// each kernels_*.cu exports one of these
+void register_f32_small(void (*add)(const KernelEntry&));
+void register_f32_large(void (*add)(const KernelEntry&));
+void register_f32_col(void (*add)(const KernelEntry&));
+void register_f64_small(void (*add)(const KernelEntry&));
+void register_f64_large(void (*add)(const KernelEntry&));
+void register_f64_col(void (*add)(const KernelEntry&));
+
+}  // namespace b200fft

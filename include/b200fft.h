@@ -1,0 +1,105 @@
+/*
+ * b200fft -- C ABI of the B200-native FFT engine that drops in for the cuFFT binding used by
+ * accelerate-fft's PTX backend.  Every entry point below replaces one symbol of Hackage
+ * `cufft` (module Foreign.CUDA.FFT) at the call site cited (paths relative to
+ * /root/reference/src/Data/Array/Accelerate/Math/FFT/LLVM/).
+ *
+ * Conventions (mirroring cuFFT so the Haskell shim is a one-line-per-call edit):
+ *   - every call returns an int status, 0 == B200FFT_SUCCESS;
+ *   - transforms are OUT-OF-PLACE (in != out), the input is never written;
+ *   - data is interleaved complex (re,im) float or double, dense row-major, last extent
+ *     contiguous (Type.hs:32, PTX.hs:99);
+ *   - results are UN-NORMALISED in both directions (FFT.hs applies the Inverse scale);
+ *   - plans are immutable after creation; b200fftExec is re-entrant, takes the stream as an
+ *     argument (no setStream race, cf. PTX.hs:121) and only enqueues work -- it never
+ *     synchronises the host;
+ *   - the library uses the CUDA context current on the calling thread and never sets a device.
+ * No cuFFT, no CPU fallback: if no GPU kernel exists for a request the call fails.
+ */
+#ifndef B200FFT_H
+#define B200FFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200fft_plan_s* b200fftHandle;      /* replaces FFT.Handle  (PTX/Plans.hs:41,42,50,66) */
+typedef void* b200fftStream;                        /* a CUstream / cudaStream_t */
+
+/* transform type tags; values equal cuFFT's so `fromEnum t` hashing stays identical (PTX.hs:126-128) */
+#define B200FFT_C2C 0x29
+#define B200FFT_Z2Z 0x69
+/* directions (PTX.hs:130-132 fftMode: Forward -> FORWARD, Reverse/Inverse -> INVERSE) */
+#define B200FFT_FORWARD (-1)
+#define B200FFT_INVERSE 1
+
+enum {
+  B200FFT_SUCCESS = 0,
+  B200FFT_INVALID_PLAN = 1,
+  B200FFT_ALLOC_FAILED = 2,
+  B200FFT_INVALID_TYPE = 3,
+  B200FFT_INVALID_VALUE = 4,
+  B200FFT_INTERNAL_ERROR = 5,
+  B200FFT_EXEC_FAILED = 6,
+  B200FFT_INVALID_SIZE = 8,
+  B200FFT_NO_DEVICE = 11,
+  B200FFT_NOT_SUPPORTED = 16
+};
+
+/* FFT.plan1D n t batch            -- PTX.hs:141 */
+int b200fftPlan1d(b200fftHandle* plan, int64_t n, int type, int64_t batch);
+/* FFT.plan2D h w t                 -- PTX.hs:148 */
+int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type);
+/* FFT.plan3D d h w t               -- PTX.hs:155 */
+int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type);
+/* FFT.planMany [n] Nothing Nothing t batch (rank 1, contiguous, idist = odist = n) -- PTX.hs:162,169 */
+int b200fftPlanMany1d(b200fftHandle* plan, int64_t n, int64_t batch, int type);
+
+/* FFT.setStream + FFT.execC2C / FFT.execZ2Z  -- PTX.hs:119-124.
+ * direction: B200FFT_FORWARD or B200FFT_INVERSE; the element type is baked into the plan. */
+int b200fftExec(b200fftHandle plan, const void* in, void* out, int direction, b200fftStream stream);
+/* Same, with every output element multiplied by `scale` in the last butterfly pass
+ * (the fused-Inverse entry of SURVEY.md section 8f-2; no reference call site yet). */
+int b200fftExecScaled(b200fftHandle plan, const void* in, void* out, int direction, double scale,
+                      b200fftStream stream);
+
+/* FFT.destroy -- PTX/Plans.hs:80.  Safe from any thread (GC finaliser). */
+int b200fftDestroy(b200fftHandle plan);
+
+const char* b200fftErrorString(int status);
+
+/* Introspection used by the bench / tests (no reference counterpart). */
+size_t b200fftScratchBytes(b200fftHandle plan);      /* stream-ordered scratch one exec allocates */
+int b200fftNumPasses(b200fftHandle plan);            /* kernel launches (= HBM passes) per exec */
+int64_t b200fftKernelLaunches(void);                 /* process-wide count of kernels launched */
+/* fills `buf` with a one-line-per-pass description of the plan; returns bytes written */
+int b200fftDescribe(b200fftHandle plan, char* buf, int buflen);
+
+/*
+ * Host-side mirror of the reference's public API for this path (FFT.hs:63-173 + PTX.hs +
+ * PTX/Plans.hs): shape/rank dispatch, Mode semantics, the five plan caches and the Inverse
+ * normalisation.  `mode`: 0 Forward, 1 Reverse, 2 Inverse (Mode.hs:15-19).
+ * `rank`/`shape`: Accelerate shape, outermost first, shape[rank-1] contiguous.
+ * Device-pointer flavour (what foreignAcc would call) ...
+ */
+int accfft_fft(int mode, int rank, const int64_t* shape, int type, const void* d_in, void* d_out,
+               b200fftStream stream);                                   /* FFT.hs:63-84  / PTX.hs:52-61 */
+int accfft_fft1D(int mode, int64_t n, int type, const void* d_in, void* d_out, b200fftStream stream);   /* FFT.hs:92-111  */
+int accfft_fft2D(int mode, int64_t h, int64_t w, int type, const void* d_in, void* d_out, b200fftStream stream); /* FFT.hs:119-142 */
+int accfft_fft3D(int mode, int64_t d, int64_t h, int64_t w, int type, const void* d_in, void* d_out,
+                 b200fftStream stream);                                 /* FFT.hs:150-173 */
+/* ... and host-buffer flavour (what `run` does around it): H2D copy, transform, D2H copy,
+ * synchronous.  kind: 0 fft (innermost axis), 1 fft1D, 2 fft2D, 3 fft3D. */
+int accfft_run_host(int kind, int mode, int rank, const int64_t* shape, int type, const void* h_in, void* h_out);
+/* when set non-zero the Inverse scale is fused into the last pass instead of a second kernel */
+void accfft_set_fused_inverse(int on);
+int accfft_plan_cache_size(void);
+void accfft_plan_cache_clear(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FFT_H */
