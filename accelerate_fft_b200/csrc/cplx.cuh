@@ -32,6 +32,12 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
 template <typename C> __device__ __forceinline__ C mul_mi(C a) { return C{a.y, -a.x}; }  // a * (-i)
 template <typename C> __device__ __forceinline__ C cswap(C a) { return C{a.y, a.x}; }
 
+// bulk data is touched once per launch: evict-first loads / stores keep the reused twiddle tables cached
+__device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double2* p, double2 v) { __stcs(p, v); }
+
 // cos(2 pi m / 32), m = 0..8  (first quadrant incl. end points), correctly rounded doubles
 __device__ __forceinline__ constexpr double cos32(int m) {
   constexpr double t[9] = {1.0,

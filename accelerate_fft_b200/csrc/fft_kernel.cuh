@@ -23,12 +23,17 @@ struct Geom {
   int swap_in, swap_out;         // inverse = swap(fwd(swap(x)))
 };
 
-template <typename T_, int N_, int E_, int TL_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
+template <typename T_, int N_, int E_, int TL_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
 struct Cfg {
   using real = T_;
   static constexpr int N = N_, E = E_, TL = TL_;
   static constexpr int TPT = N / E;            // threads per line
   static constexpr int THREADS = TPT * TL;
+  // min resident CTAs per SM the register allocation must allow; 0 = derive from a register target of
+  // 64 (c64 E<=16, c128 E<=8) or 128 (c64 E=32, c128 E=16) per thread
+  static constexpr int TARGET_REGS = (sizeof(T_) == 4) ? (E_ <= 16 ? 64 : 128) : (E_ <= 8 ? 64 : 128);
+  static constexpr int AUTO_MINB = 65536 / (TARGET_REGS * THREADS) < 1 ? 1 : (65536 / (TARGET_REGS * THREADS) > 16 ? 16 : 65536 / (TARGET_REGS * THREADS));
+  static constexpr int MINB = MINB_ > 0 ? MINB_ : AUTO_MINB;
   static constexpr int rad[4] = {R0_, R1_, R2_, R3_};
   static constexpr int S = (R3_ > 1) ? 4 : (R2_ > 1) ? 3 : (R1_ > 1) ? 2 : 1;
   static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
@@ -122,7 +127,7 @@ __device__ __forceinline__ void stages(C (&v)[K::E], C* sm, int& l, int& t, cons
 // LLF: load mapping is line-fastest (adjacent threads = adjacent lines; use when ils == 1)
 // SLF: same for the store side (ols == 1).   TW4: multiply the result by the four-step twiddle.
 template <class K, bool LLF, bool SLF, bool TW4>
-__global__ void __launch_bounds__(K::THREADS)
+__global__ void __launch_bounds__(K::THREADS, K::MINB)
 fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
                  const cpx_t<typename K::real>* __restrict__ tws, const cpx_t<typename K::real>* __restrict__ tw_lo,
                  const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale) {
@@ -150,7 +155,7 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
     const long long step = (long long)K::TPT * g.ins;
     static_for<0, K::E>([&](auto ec) {
       constexpr int e = ec;
-      v[e] = valid ? ip[e * step] : C{0, 0};
+      v[e] = valid ? ld_stream(ip + e * step) : C{0, 0};
     });
     if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
   }
@@ -174,7 +179,7 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
     if (g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
     C* op = out + (long long)b * g.obs + (long long)o * g.oos + (long long)line * g.ols + (long long)t * g.ons;
     const long long step = (long long)K::TPT * g.ons;
-    if (valid) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; op[e * step] = v[e]; });
+    if (valid) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; st_stream(op + e * step, v[e]); });
   }
 }
 

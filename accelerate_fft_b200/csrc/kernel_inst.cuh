@@ -12,6 +12,7 @@ KernelEntry make_entry() {
   e.N = K::N; e.E = K::E; e.TL = K::TL; e.threads = K::THREADS;
   e.flavor = (LLF && SLF) ? FL_COL : (!LLF && SLF) ? FL_TRANS : FL_ROW;
   e.tw4 = TW4;
+  e.minb = K::MINB;
   e.smem = K::template smem_bytes<(LLF && SLF)>();
   e.S = K::S;
   for (int i = 0; i < 4; i++) e.rad[i] = K::rad[i];

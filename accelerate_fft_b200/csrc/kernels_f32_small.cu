@@ -2,15 +2,15 @@
 #include "kernel_inst.cuh"
 namespace b200fft {
 void register_f32_small(void (*add)(const KernelEntry&)) {
-  REG_ROW(float, 2, 2, 128, 2);
-  REG_ROW(float, 4, 4, 128, 4);
-  REG_ROW(float, 8, 8, 128, 8);
-  REG_ROW(float, 16, 16, 128, 16);
-  REG_ROW(float, 32, 8, 32, 8, 4);
-  REG_ROW(float, 64, 8, 16, 8, 8);
-  REG_ROW(float, 128, 16, 16, 16, 8);
-  REG_ROW(float, 256, 16, 8, 16, 16);
-  REG_ROW(float, 512, 16, 4, 16, 16, 2);
-  REG_ROW(float, 1024, 16, 2, 16, 16, 4);
+  REG_ROW(float, 2, 2, 128, 0, 2);
+  REG_ROW(float, 4, 4, 128, 0, 4);
+  REG_ROW(float, 8, 8, 128, 0, 8);
+  REG_ROW(float, 16, 16, 128, 0, 16);
+  REG_ROW(float, 32, 8, 32, 0, 8, 4);
+  REG_ROW(float, 64, 8, 16, 0, 8, 8);
+  REG_ROW(float, 128, 16, 16, 0, 16, 8);
+  REG_ROW(float, 256, 16, 8, 0, 16, 16);
+  REG_ROW(float, 512, 16, 4, 0, 16, 16, 2);
+  REG_ROW(float, 1024, 16, 2, 0, 16, 16, 4);
 }
 }  // namespace b200fft

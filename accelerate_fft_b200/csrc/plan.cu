@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -28,7 +29,13 @@ static std::vector<KernelEntry>& reg() {
   static std::vector<KernelEntry> r;
   return r;
 }
-static void add_entry(const KernelEntry& e) { reg().push_back(e); }
+static void add_entry(const KernelEntry& e_) {
+  KernelEntry e = e_;
+  e.variant = 0;
+  for (const auto& o : reg())
+    if (o.is_double == e.is_double && o.N == e.N && o.flavor == e.flavor && o.tw4 == e.tw4) e.variant++;
+  reg().push_back(e);
+}
 static std::once_flag g_reg_once;
 static void ensure_registry() {
   std::call_once(g_reg_once, [] {
@@ -41,15 +48,32 @@ static void ensure_registry() {
   });
 }
 
+// Developer override: B200FFT_VARIANTS="r4096d=1,c1024f=2" picks registration-order variant 1 of the
+// c128 row kernel for N=4096, etc. (flavour r/c/t, N, type f/d).  Default is variant 0.
+static int forced_variant(int is_double, int N, int flavor) {
+  const char* env = getenv("B200FFT_VARIANTS");
+  if (!env) return 0;
+  char key[64];
+  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : 't', N, is_double ? 'd' : 'f');
+  const char* p = env;
+  while ((p = strstr(p, key)) != nullptr) {
+    if (p == env || p[-1] == ',') return atoi(p + strlen(key));
+    p++;
+  }
+  return 0;
+}
+
 const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int prefer_tl) {
   ensure_registry();
-  const KernelEntry* best = nullptr;
+  (void)prefer_tl;
+  const int want = forced_variant(is_double, N, flavor);
+  const KernelEntry* first = nullptr;
   for (const auto& e : reg()) {
     if (e.is_double != is_double || e.N != N || e.flavor != flavor || e.tw4 != tw4) continue;
-    if (!best) best = &e;
-    else if (prefer_tl > 0 && std::abs(e.TL - prefer_tl) < std::abs(best->TL - prefer_tl)) best = &e;
+    if (!first) first = &e;
+    if (e.variant == want) return &e;
   }
-  return best;
+  return first;
 }
 int list_kernels(const KernelEntry** out, int max) {
   ensure_registry();
@@ -194,8 +218,8 @@ struct Builder {
     ps.ntiles = (long long)g.nb * g.no * ps.g.ntl;
     if (ps.ntiles >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return false; }
     char buf[256];
-    snprintf(buf, sizeof buf, "%s: lines N=%d E=%d TL=%d %s%s radix=%dx%dx%dx%d threads=%d smem=%zu tiles=%lld", what, k->N,
-             k->E, k->TL, flavor == FL_ROW ? "row" : flavor == FL_COL ? "col" : "trans", tw4 ? "+tw" : "", k->rad[0], k->rad[1],
+    snprintf(buf, sizeof buf, "%s: lines N=%d v%d E=%d TL=%d minb=%d %s%s radix=%dx%dx%dx%d threads=%d smem=%zu tiles=%lld", what, k->N,
+             k->variant, k->E, k->TL, k->minb, flavor == FL_ROW ? "row" : flavor == FL_COL ? "col" : "trans", tw4 ? "+tw" : "", k->rad[0], k->rad[1],
              k->rad[2], k->rad[3], k->threads, k->smem, ps.ntiles);
     ps.desc = buf;
     push(ps);

@@ -12,6 +12,8 @@ struct KernelEntry {
   int N, E, TL, threads;
   int flavor;      // FL_ROW: rows in / rows out; FL_COL: line-fastest both; FL_TRANS: rows in / line-fastest out
   int tw4;         // multiplies by the four-step twiddle at the store
+  int variant;     // registration order among entries with the same (type, N, flavor, tw4); 0 is the default
+  int minb;
   size_t smem;
   int S, rad[4];
   int tw_len;      // stage twiddle table length (complex elements)

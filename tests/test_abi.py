@@ -1,0 +1,87 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/b200fft.h declares, and fails loudly (no fallback) when there is no device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200fft.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:b200fft|accfft_)\w+)\s*\(", src)))
+
+
+def test_header_declares_the_cufft_replacements():
+    syms = declared_symbols()
+    for s in ("b200fftPlan1d", "b200fftPlan2d", "b200fftPlan3d", "b200fftPlanMany1d", "b200fftExec", "b200fftDestroy",
+              "b200fftErrorString", "accfft_fft", "accfft_fft1D", "accfft_fft2D", "accfft_fft3D"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(af):
+    L = af.lib()
+    for s in declared_symbols():
+        assert hasattr(L, s), "libb200fft.so does not export %s" % s
+
+
+def test_library_has_no_cufft_or_cublas_dependency():
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(ROOT, "accelerate_fft_b200", "libb200fft.so")], capture_output=True, text=True).stdout
+    assert "cufft" not in out.lower() and "cublas" not in out.lower()
+
+
+def test_error_strings(af):
+    L = af.lib()
+    assert L.b200fftErrorString(0) == b"B200FFT_SUCCESS"
+    assert b"NO_DEVICE" in L.b200fftErrorString(11)
+    assert b"UNKNOWN" in L.b200fftErrorString(12345)
+
+
+def test_argument_validation_without_device(af):
+    L = af.lib()
+    h = ctypes.c_void_p()
+    assert L.b200fftPlanMany1d(ctypes.byref(h), 1024, 4, 0x1234) == 3      # INVALID_TYPE
+    assert L.b200fftPlanMany1d(ctypes.byref(h), 0, 4, af.C2C) == 8         # INVALID_SIZE
+    assert L.b200fftPlan2d(ctypes.byref(h), -1, 4, af.Z2Z) == 8
+    assert L.b200fftPlanMany1d(None, 8, 1, af.C2C) == 4                    # INVALID_VALUE
+    assert L.b200fftExec(None, None, None, -1, None) == 1                  # INVALID_PLAN
+    assert L.b200fftDestroy(None) == 1
+
+
+def test_no_cpu_fallback(af):
+    """Without a GPU the product must refuse, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(af.B200FFTError) as ei:
+        af.run_host("fft", "Forward", np.ones((2, 8), np.complex64))
+    assert ei.value.status == 11
+    with pytest.raises(RuntimeError):
+        af.fft("Forward", torch.ones(8, dtype=torch.complex64))
+    h = ctypes.c_void_p()
+    assert af.lib().b200fftPlanMany1d(ctypes.byref(h), 1024, 4, af.C2C) == 11
+
+
+def test_python_surface_mirrors_reference(af):
+    import torch
+    assert af.signOfMode(af.Forward) == -1 and af.signOfMode(af.Reverse) == 1 and af.signOfMode(af.Inverse) == 1
+    with pytest.raises((TypeError, RuntimeError)):
+        af.fft("Forward", torch.ones(8, dtype=torch.float32))
+    with pytest.raises(ValueError):
+        af.fft2D("Forward", torch.ones(8, dtype=torch.complex64))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing in the package may reference it."""
+    pkg = os.path.join(ROOT, "accelerate_fft_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f

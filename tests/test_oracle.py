@@ -1,0 +1,137 @@
+"""CPU tests of the oracle (oracle/): the restatement of Adhoc.hs is pinned against the committed
+known-answer vectors, the exact long-double definition, independent library FFTs, and the seven
+algebraic properties of the reference's own suite (test/Test/FFT.hs:112-236)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.fft as sf
+
+from conftest import bar, rand_complex, rel_l2
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "kat.npz"))
+SIZES_1D = sorted(int(k.split("_")[1]) for k in GOLD.files if k.startswith("in1_"))
+# the reference's Float Bluestein branch forms its chirp angle in single precision and is only ~1e-4
+# accurate near n~1000; the oracle restates that faithfully, so sizes that take
+# the chirp branch are held to a looser bar in Float.
+def _is_5smooth(n):
+    for p in (2, 3, 5):
+        while n % p == 0:
+            n //= p
+    return n == 1
+
+
+@pytest.mark.parametrize("n", SIZES_1D)
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_oracle_matches_golden_1d(oracle, n, dtype):
+    x = GOLD[f"in1_{n}"].astype(dtype)
+    ref = GOLD[f"fwd1_{n}" + ("_f32" if dtype == np.complex64 else "")]
+    y = oracle.adhoc_fft(-1, x)
+    tol = bar(dtype, n) if _is_5smooth(n) else (5e-4 if dtype == np.complex64 else 1e-12)
+    assert rel_l2(y, ref) <= tol
+    # Reverse of the forward output gives n*x back (Mode.hs: Reverse is un-normalised)
+    z = oracle.adhoc_fft(+1, y)
+    assert rel_l2(z, n * x.astype(np.complex128)) <= 2 * tol
+
+
+@pytest.mark.parametrize("key", [k[4:] for k in GOLD.files if k.startswith("in2_")])
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_oracle_matches_golden_2d(oracle, key, dtype):
+    x = GOLD["in2_" + key].astype(dtype)
+    ref = GOLD["fwd2_" + key + ("_f32" if dtype == np.complex64 else "")]
+    assert rel_l2(oracle.fft2D("Forward", x), ref) <= bar(dtype, x.size)
+
+
+@pytest.mark.parametrize("key", [k[4:] for k in GOLD.files if k.startswith("in3_")])
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_oracle_matches_golden_3d(oracle, key, dtype):
+    x = GOLD["in3_" + key].astype(dtype)
+    ref = GOLD["fwd3_" + key + ("_f32" if dtype == np.complex64 else "")]
+    assert rel_l2(oracle.fft3D("Forward", x), ref) <= bar(dtype, x.size)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 64, 256, 12, 45, 100])
+def test_closed_form_vectors(oracle, n):
+    """delta_m -> e^{-+2 pi i m k/n}; constant -> n*delta_0; single tone -> delta."""
+    k = np.arange(n)
+    for sign, mode in ((-1, "Forward"), (+1, "Reverse")):
+        for m in {0, 1 % n, n // 2, n - 1}:
+            d = np.zeros(n, np.complex128)
+            d[m] = 1
+            assert rel_l2(oracle.fft1D(mode, d), np.exp(sign * 2j * np.pi * m * k / n)) < 1e-13
+        c = np.full(n, 0.5 - 0.25j)
+        e = np.zeros(n, np.complex128)
+        e[0] = n * (0.5 - 0.25j)
+        assert rel_l2(oracle.fft1D(mode, c), e) < 1e-13
+        f = 3 % n
+        tone = np.exp(-sign * 2j * np.pi * f * k / n)
+        e = np.zeros(n, np.complex128)
+        e[f] = n
+        assert rel_l2(oracle.fft1D(mode, tone), e) < 1e-12
+
+
+@pytest.mark.parametrize("n", [2, 3, 8, 17, 60, 128, 243])
+def test_oracle_vs_exact_definition(oracle, n):
+    rng = np.random.default_rng(n)
+    x = rand_complex(rng, (3, n), np.complex128)
+    for sign in (-1, 1):
+        ex = oracle.exact_dft(sign, x)
+        assert oracle.rel_l2(oracle.adhoc_fft(sign, x), ex) <= (bar(np.complex128, n) if _is_5smooth(n) else 1e-12)
+        # the exact definition agrees with an independent library in long double
+        lib = sf.fft(x.astype(np.clongdouble)) if sign < 0 else sf.ifft(x.astype(np.clongdouble)) * n
+        assert oracle.rel_l2(ex, lib) < 1e-17 * n
+    assert abs(oracle.exact_bin(-1, x[0], 1 % n) - oracle.exact_dft(-1, x[0:1])[0, 1 % n]) < 1e-16 * n
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_oracle_baseline_shapes_vs_library(oracle, dtype):
+    """cfg1 / cfg2 row lengths against pocketfft (stand-in for the reference's FFTW path)."""
+    rng = np.random.default_rng(1001)
+    for n in (1024, 4096):
+        x = rand_complex(rng, (8, n), dtype)
+        ref = sf.fft(x.astype(np.clongdouble)).astype(np.complex128)
+        e = rel_l2(oracle.fft("Forward", x), ref)
+        assert e <= bar(dtype, n) / 10
+        lib = sf.fft(x)  # working precision library
+        assert rel_l2(lib, ref) <= bar(dtype, n) / 10
+
+
+def test_inverse_scaling(oracle):
+    """FFT.hs:83,110,141,172: Inverse divides by innermost length (fft), length (fft1D), size (fft2D/3D)."""
+    rng = np.random.default_rng(5)
+    x = rand_complex(rng, (4, 6, 8), np.complex128)
+    assert rel_l2(oracle.fft("Inverse", x), np.fft.ifft(x, axis=-1)) < 1e-14
+    assert rel_l2(oracle.fft("Reverse", x), np.fft.ifft(x, axis=-1) * 8) < 1e-14
+    assert rel_l2(oracle.fft1D("Inverse", x[0, 0]), np.fft.ifft(x[0, 0])) < 1e-14
+    assert rel_l2(oracle.fft2D("Inverse", x[0]), np.fft.ifft2(x[0])) < 1e-14
+    assert rel_l2(oracle.fft3D("Inverse", x), np.fft.ifftn(x)) < 1e-14
+    assert rel_l2(oracle.fft3D("Reverse", x), np.fft.ifftn(x) * x.size) < 1e-14
+
+
+# ---- the reference's seven properties (test/Test/FFT.hs:112-236), on the oracle ---------------
+
+def _rev(a):  # reverse :86-94 : rev[k] = x[(-k) mod n] along the innermost axis
+    n = a.shape[-1]
+    return a[..., (-np.arange(n)) % n]
+
+
+@pytest.mark.parametrize("shape", [(1,), (7,), (64,), (100,), (5, 12), (3, 4, 6)])
+@pytest.mark.parametrize("mode", ["Forward", "Reverse", "Inverse"])
+def test_reference_properties_on_oracle(oracle, shape, mode):
+    rng = np.random.default_rng(hash((shape, mode)) % 2**32)
+    x = rand_complex(rng, shape, np.complex128)
+    y = rand_complex(rng, shape, np.complex128)
+    c = complex(rng.uniform(-1, 1), rng.uniform(-1, 1))
+    full = {1: oracle.fft1D, 2: oracle.fft2D, 3: oracle.fft3D}[len(shape)]
+    tol = 1e-12
+    assert rel_l2(full(mode, c * x), c * full(mode, x)) < tol                      # homogeneity
+    assert rel_l2(full(mode, x + y), full(mode, x) + full(mode, y)) < tol          # additivity
+    assert rel_l2(full("Inverse", full("Forward", x)), x) < tol                    # inverse
+    F = lambda a: oracle.fft(mode, a)
+    n = shape[-1]
+    assert rel_l2(_rev(F(x)), F(_rev(x))) < tol                                    # reverse
+    assert rel_l2(np.conj(F(x)), F(np.conj(_rev(x)))) < tol                        # conjugate
+    if mode != "Inverse":
+        nx = np.sqrt((np.abs(x) ** 2).sum(-1))
+        assert np.allclose(np.sqrt((np.abs(F(x)) ** 2).sum(-1)), np.sqrt(n) * nx, rtol=1e-12)   # isometry
+        assert np.allclose((F(x) * np.conj(F(y))).sum(-1), n * (x * np.conj(y)).sum(-1), rtol=1e-10, atol=1e-10)  # unitarity

@@ -1,0 +1,353 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (accfft_* / b200fft*), against the
+oracle (oracle/: C restatement of Adhoc.hs + exact long-double DFT), the committed known-answer
+vectors, and -- at BASELINE.json's full sizes -- size-independent properties.
+
+Tolerance everywhere: relative L2 <= 1e-5*log2(N) for Float, 1e-13*log2(N) for Double
+(N = points of one transform), as stated in BASELINE.json's north_star."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bar, rand_complex, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "kat.npz"))
+DTYPES = [np.complex64, np.complex128]
+MODES = ["Forward", "Reverse", "Inverse"]
+
+
+def gpu(af, kind, mode, x):
+    import torch
+    f = {"fft": af.fft, "fft1D": af.fft1D, "fft2D": af.fft2D, "fft3D": af.fft3D}[kind]
+    return f(mode, torch.from_numpy(np.ascontiguousarray(x)).cuda()).cpu().numpy()
+
+
+def _is_5smooth(n):
+    for p in (2, 3, 5):
+        while n % p == 0:
+            n //= p
+    return n == 1
+
+
+# ---- committed known-answer vectors ------------------------------------------------------------
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_golden_vectors(af, dtype):
+    suf = "_f32" if dtype == np.complex64 else ""
+    for k in GOLD.files:
+        if not k.startswith("in"):
+            continue
+        rank = int(k[2])
+        x = GOLD[k].astype(dtype)
+        ref = GOLD["fwd" + k[2:] + suf]
+        if rank == 1:
+            y = gpu(af, "fft", "Forward", x)
+            n = x.shape[-1]
+        else:
+            y = gpu(af, "fft%dD" % rank, "Forward", x)
+            n = x.size
+        assert rel_l2(y, ref) <= bar(dtype, n), k
+
+
+# ---- against the oracle on seeded inputs ---------------------------------------------------------
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_fft_pow2_vs_oracle(af, oracle, dtype, mode):
+    rng = np.random.default_rng(11)
+    for lg in range(0, 15):
+        n = 1 << lg
+        if dtype == np.complex128 and n > 8192:
+            continue
+        x = rand_complex(rng, (5, n), dtype)
+        y = gpu(af, "fft", mode, x)
+        ref = oracle.fft(mode, x, threads=4)
+        assert rel_l2(y, ref) <= bar(dtype, n), (n, mode)
+        ex = oracle.exact_dft(oracle.sign_of_mode(mode), x[:1]) if n <= 2048 else None
+        if ex is not None:
+            if mode == "Inverse":
+                ex = ex / n
+            assert rel_l2(y[:1], ex.astype(np.complex128)) <= bar(dtype, n) / 2, (n, mode)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fft_every_length_1_to_130_and_reference_range(af, oracle, dtype):
+    """cuFFT accepts every length; the reference's PTX suite draws n in [1,1024] (test/Test/Base.hs:44-45)."""
+    rng = np.random.default_rng(12)
+    sizes = list(range(1, 131)) + [243, 255, 257, 360, 509, 625, 729, 1000, 1009, 1021, 1023]
+    for n in sizes:
+        x = rand_complex(rng, (3, n), dtype)
+        y = gpu(af, "fft", "Forward", x)
+        ex = oracle.exact_dft(-1, x).astype(np.complex128)
+        assert rel_l2(y, ex) <= bar(dtype, n), n
+        if _is_5smooth(n):  # the oracle's chirp branch is only ~1e-4 accurate in Float
+            assert rel_l2(y, oracle.fft("Forward", x)) <= bar(dtype, n), n
+        z = gpu(af, "fft", "Inverse", y.astype(dtype))
+        assert rel_l2(z, x) <= 2 * bar(dtype, n), n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_large_1d_four_step_vs_library(af, dtype):
+    import scipy.fft as sf
+    rng = np.random.default_rng(13)
+    for n in (1 << 15, 1 << 18, 1 << 21, 3 << 16, 1000003):
+        x = rand_complex(rng, (n,), dtype)
+        y = gpu(af, "fft1D", "Forward", x)
+        ref = sf.fft(x.astype(np.complex128), workers=-1)
+        assert rel_l2(y, ref) <= bar(dtype, n), n
+        z = gpu(af, "fft1D", "Inverse", y.astype(dtype))
+        assert rel_l2(z, x) <= 2 * bar(dtype, n), n
+
+
+SHAPES_2D = [(1, 1), (1, 16), (16, 1), (8, 8), (48, 128), (128, 48), (37, 64), (64, 37), (100, 100), (31, 17), (512, 256),
+             (4096, 16), (16, 4096), (8192, 4), (2, 16384)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_fft2d_vs_oracle(af, oracle, dtype, mode):
+    rng = np.random.default_rng(14)
+    for shape in SHAPES_2D:
+        if dtype == np.complex128 and max(shape) > 8192:
+            continue
+        x = rand_complex(rng, shape, dtype)
+        y = gpu(af, "fft2D", mode, x)
+        x128 = x.astype(np.complex128)
+        ex = np.fft.fft2(x128) if mode == "Forward" else np.fft.ifft2(x128) * (1 if mode == "Inverse" else x.size)
+        assert rel_l2(y, ex) <= bar(dtype, x.size), (shape, mode)
+        if all(_is_5smooth(s) for s in shape):
+            assert rel_l2(y, oracle.fft2D(mode, x, threads=4)) <= bar(dtype, x.size), (shape, mode)
+
+
+SHAPES_3D = [(1, 1, 1), (2, 2, 2), (16, 32, 64), (64, 32, 16), (10, 12, 14), (3, 5, 7), (5, 64, 33), (4, 1024, 8), (1024, 4, 8),
+             (64, 64, 64), (16, 16, 4096)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_fft3d_vs_oracle(af, oracle, dtype, mode):
+    rng = np.random.default_rng(15)
+    for shape in SHAPES_3D:
+        x = rand_complex(rng, shape, dtype)
+        y = gpu(af, "fft3D", mode, x)
+        x128 = x.astype(np.complex128)
+        ex = np.fft.fftn(x128) if mode == "Forward" else np.fft.ifftn(x128) * (1 if mode == "Inverse" else x.size)
+        assert rel_l2(y, ex) <= bar(dtype, x.size), (shape, mode)
+        if all(_is_5smooth(s) for s in shape) and x.size <= 1 << 18:
+            assert rel_l2(y, oracle.fft3D(mode, x, threads=4)) <= bar(dtype, x.size), (shape, mode)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fft_innermost_axis_of_rank_2_3_4(af, oracle, dtype):
+    """FFT.hs:63-84 `fft` transforms only the innermost axis; rank 2/3 use the batched plans (PTX.hs:59-60)."""
+    rng = np.random.default_rng(16)
+    for shape in [(7, 64), (3, 5, 128), (4, 6, 100), (2, 3, 4, 32)]:
+        x = rand_complex(rng, shape, dtype)
+        for mode in MODES:
+            assert rel_l2(gpu(af, "fft", mode, x), oracle.fft(mode, x)) <= bar(dtype, shape[-1]), (shape, mode)
+
+
+def test_edge_cases(af):
+    import torch
+    # empty arrays: nothing to do, shape preserved
+    e = torch.empty((0, 16), dtype=torch.complex64, device="cuda")
+    assert af.fft("Forward", e).shape == (0, 16)
+    # length-1 transforms are the identity (Adhoc.hs:45)
+    x = torch.randn(9, 1, dtype=torch.complex128, device="cuda")
+    assert torch.equal(af.fft("Forward", x), x)
+    assert torch.equal(af.fft("Inverse", x), x)
+    # the input is never written (out-of-place contract, PTX.hs:92)
+    a = torch.randn(64, 4096, dtype=torch.complex64, device="cuda")
+    b = a.clone()
+    af.fft2D("Inverse", a)
+    assert torch.equal(a, b)
+    # non-contiguous input is accepted (made dense, like Accelerate's arrays always are)
+    t = torch.randn(32, 48, dtype=torch.complex64, device="cuda").t()
+    y = af.fft("Forward", t)
+    assert rel_l2(y.cpu().numpy(), np.fft.fft(t.cpu().numpy().astype(np.complex128), axis=-1)) < 1e-5
+
+
+def test_host_buffer_entry_and_fused_inverse(af, oracle):
+    rng = np.random.default_rng(17)
+    x = rand_complex(rng, (6, 10, 256), np.complex64)
+    assert rel_l2(af.run_host("fft", "Forward", x), oracle.fft("Forward", x)) <= bar(np.complex64, 256)
+    x2 = rand_complex(rng, (96, 80), np.complex128)
+    ref = oracle.fft2D("Inverse", x2)
+    assert rel_l2(af.run_host("fft2D", "Inverse", x2), ref) <= bar(np.complex128, x2.size)
+    af.set_fused_inverse(True)
+    try:
+        assert rel_l2(af.run_host("fft2D", "Inverse", x2), ref) <= bar(np.complex128, x2.size)
+        x3 = rand_complex(rng, (1 << 16,), np.complex64)
+        assert rel_l2(af.run_host("fft1D", "Inverse", x3), np.fft.ifft(x3.astype(np.complex128))) <= bar(np.complex64, 1 << 16)
+    finally:
+        af.set_fused_inverse(False)
+
+
+def test_plan_cache_and_streams(af):
+    """Plans are cached per (context, shape, type) (PTX/Plans.hs:66-86) and exec takes the stream as an argument."""
+    import torch
+    af.lib().accfft_plan_cache_clear()
+    x = torch.randn(16, 512, dtype=torch.complex64, device="cuda")
+    af.fft("Forward", x)
+    n1 = af.lib().accfft_plan_cache_size()
+    af.fft("Inverse", x)          # same shape, other direction: same plan
+    assert af.lib().accfft_plan_cache_size() == n1
+    af.fft("Forward", x.to(torch.complex128))
+    assert af.lib().accfft_plan_cache_size() == n1 + 1
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    ref = torch.fft.fft(x.to(torch.complex128), dim=-1)  # test-side reference only
+    outs = []
+    for s in (s1, s2, s1, s2):
+        with torch.cuda.stream(s):
+            outs.append(af.fft("Forward", x))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert rel_l2(o.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+# ---- BASELINE.json configurations at full size ---------------------------------------------------
+
+def test_cfg1_full_vs_oracle(af, oracle):
+    """cfg 1: c64 [4096,1024] Forward -- full-array compare with both CPU paths."""
+    import scipy.fft as sf
+    rng = np.random.default_rng(1001)
+    x = rand_complex(rng, (4096, 1024), np.complex64)
+    y = gpu(af, "fft", "Forward", x)
+    assert rel_l2(y, oracle.fft("Forward", x, threads=8)) <= bar(np.complex64, 1024)              # pure-Accelerate path
+    assert rel_l2(y, sf.fft(x.astype(np.complex128), workers=-1)) <= bar(np.complex64, 1024) / 4  # FFTW stand-in, exact-ish
+
+
+def test_cfg2_full_size(af, oracle):
+    """cfg 2: c128 [65536,4096] Forward + Inverse.  Sampled rows against the oracle and the exact
+    long-double transform; whole-array round trip, Parseval and linearity on the device."""
+    import scipy.fft as sf
+    import torch
+    n, batch = 4096, 65536
+    g = torch.Generator(device="cuda").manual_seed(1002)
+    x = (torch.rand(batch, n, 2, dtype=torch.float64, device="cuda", generator=g) * 2 - 1)
+    x = torch.view_as_complex(x)
+    y = af.fft("Forward", x)
+    rows = torch.tensor(sorted({0, 1, 255, 4097, 32768, 65535} | set(np.random.default_rng(2).integers(0, batch, 58).tolist())), device="cuda")
+    xs, ys = x[rows].cpu().numpy(), y[rows].cpu().numpy()
+    assert rel_l2(ys, oracle.fft("Forward", xs, threads=8)) <= bar(np.complex128, n)
+    ex = sf.fft(xs.astype(np.clongdouble)).astype(np.complex128)
+    assert rel_l2(ys, ex) <= bar(np.complex128, n) / 2
+    # Parseval per row: ||F x||^2 = n ||x||^2  (isometry property, test/Test/FFT.hs:201-217)
+    e_in = (x.real ** 2 + x.imag ** 2).sum(-1)
+    e_out = (y.real ** 2 + y.imag ** 2).sum(-1)
+    assert float(((e_out - n * e_in).abs() / (n * e_in)).max()) < 1e-12
+    z = af.fft("Inverse", y)                      # includes the 1/n scale (FFT.hs:83)
+    err = torch.linalg.vector_norm(z - x) / torch.linalg.vector_norm(x)
+    assert float(err) <= 2 * bar(np.complex128, n)
+    del z, e_in, e_out
+    # linearity with a complex scalar on the whole array
+    c = complex(0.3, -0.7)
+    y2 = af.fft("Forward", x * c)
+    err = torch.linalg.vector_norm(y2 - y * c) / torch.linalg.vector_norm(y)
+    assert float(err) <= bar(np.complex128, n)
+
+
+def test_cfg3_full_vs_library(af, oracle):
+    """cfg 3: c64 8192x8192 fft2D Forward -- full-array compare against a double-precision library transform,
+    the oracle on an embedded 256x256 problem, and the round trip."""
+    import scipy.fft as sf
+    import torch
+    rng = np.random.default_rng(1003)
+    x = rand_complex(rng, (8192, 8192), np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    yd = af.fft2D("Forward", xd)
+    y = yd.cpu().numpy()
+    ref = sf.fft2(x.astype(np.complex128), workers=-1)
+    assert rel_l2(y, ref) <= bar(np.complex64, x.size)
+    del ref
+    zd = af.fft2D("Inverse", yd)
+    assert float(torch.linalg.vector_norm(zd - xd) / torch.linalg.vector_norm(xd)) <= 2 * bar(np.complex64, x.size)
+    xs = x[:256, :256].copy()
+    assert rel_l2(gpu(af, "fft2D", "Forward", xs), oracle.fft2D("Forward", xs, threads=8)) <= bar(np.complex64, xs.size)
+
+
+def _fold(x, axis, m):
+    """sum_{j} x[n + j*m] along `axis` (length m result): the DFT of the folded sequence equals the
+    DFT of x sampled at every (len/m)-th bin."""
+    import torch
+    shp = list(x.shape)
+    L = shp[axis]
+    new = shp[:axis] + [L // m, m] + shp[axis + 1:]
+    return x.reshape(new).to(torch.complex128).sum(dim=axis)
+
+
+def test_cfg4_full_size(af, oracle):
+    """cfg 4: c64 n=2^28 fft1D.  Closed-form tones, the folding (bin-decimation) identity against the
+    oracle on random data, round trip; plus a full compare at 2^24 against a library transform."""
+    import scipy.fft as sf
+    import torch
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(1004)
+    x = torch.view_as_complex(torch.rand(n, 2, dtype=torch.float32, device="cuda", generator=g) * 2 - 1)
+    y = af.fft1D("Forward", x)
+    # folding: X[k * 2^14] for k < 2^14 == DFT_{2^14}( sum_j x[i + j*2^14] )
+    m = 1 << 14
+    folded = _fold(x, 0, m).cpu().numpy()
+    ref = oracle.exact_dft(-1, folded[None, :])[0].astype(np.complex128) if m <= 2048 else sf.fft(folded.astype(np.clongdouble)).astype(np.complex128)
+    got = y[:: n // m].cpu().numpy()
+    assert rel_l2(got, ref) <= bar(np.complex64, n)
+    assert rel_l2(oracle.fft("Forward", folded.astype(np.complex128)), ref) < 1e-12   # the oracle agrees on the folded problem
+    # offset folding catches errors in the other residue classes: X[k*2^14 + r] via modulated fold
+    r = 12345
+    ph = torch.exp(-2j * torch.pi * r * torch.arange(n, device="cuda", dtype=torch.float64) / n)
+    folded_r = _fold(x.to(torch.complex128) * ph, 0, m).cpu().numpy()
+    got_r = y[r:: n // m].cpu().numpy()
+    assert rel_l2(got_r, sf.fft(folded_r.astype(np.clongdouble)).astype(np.complex128)) <= bar(np.complex64, n)
+    del ph
+    z = af.fft1D("Inverse", y)
+    assert float(torch.linalg.vector_norm(z - x) / torch.linalg.vector_norm(x)) <= 2 * bar(np.complex64, n)
+    del z, y
+    # tones: x[j] = e^{2 pi i f j / n} -> n * delta_f
+    for f in (1, 98765, n - 3):
+        j = torch.arange(n, device="cuda", dtype=torch.float64)
+        ang = 2 * torch.pi * ((j * f) % n) / n
+        t = torch.complex(torch.cos(ang), torch.sin(ang)).to(torch.complex64)
+        del j, ang
+        yt = af.fft1D("Forward", t)
+        peak = yt[f].item()
+        assert abs(peak - n) / n < 1e-5
+        yt[f] = 0
+        assert float(torch.linalg.vector_norm(yt)) / n < 1e-4   # everything else is rounding noise of the float input
+        del t, yt
+    # full compare at 2^24
+    rng = np.random.default_rng(1004)
+    xs = rand_complex(rng, (1 << 24,), np.complex64)
+    assert rel_l2(gpu(af, "fft1D", "Forward", xs), sf.fft(xs.astype(np.complex128), workers=-1)) <= bar(np.complex64, 1 << 24)
+
+
+def test_cfg5_full_size(af, oracle):
+    """cfg 5: c64 1024^3 fft3D (single GPU).  Folding identity per axis against the oracle's fft3D,
+    plane-wave known answers, round trip."""
+    import torch
+    d = 1024
+    g = torch.Generator(device="cuda").manual_seed(1005)
+    x = torch.view_as_complex(torch.rand(d, d, d, 2, dtype=torch.float32, device="cuda", generator=g) * 2 - 1)
+    y = af.fft3D("Forward", x)
+    m = 16
+    f = _fold(_fold(_fold(x, 2, m), 1, m), 0, m).cpu().numpy()   # 16^3, complex128
+    ref = oracle.fft3D("Forward", f)
+    got = y[:: d // m, :: d // m, :: d // m].cpu().numpy()
+    assert rel_l2(got, ref) <= bar(np.complex64, d ** 3)
+    z = af.fft3D("Inverse", y)
+    assert float(torch.linalg.vector_norm(z - x) / torch.linalg.vector_norm(x)) <= 2 * bar(np.complex64, d ** 3)
+    del z, y, x
+    # plane wave e^{2 pi i (a z + b y + c x)/d} -> d^3 at (a,b,c)
+    a, b, c = 3, 1000, 517
+    i = torch.arange(d, device="cuda", dtype=torch.float64)
+    wz = torch.exp(2j * torch.pi * ((a * i) % d) / d)
+    wy = torch.exp(2j * torch.pi * ((b * i) % d) / d)
+    wx = torch.exp(2j * torch.pi * ((c * i) % d) / d)
+    t = (wz[:, None, None] * wy[None, :, None] * wx[None, None, :]).to(torch.complex64)
+    yt = af.fft3D("Forward", t)
+    del t
+    peak = yt[a, b, c].item()
+    assert abs(peak - d ** 3) / d ** 3 < 1e-5
+    yt[a, b, c] = 0
+    assert float(torch.linalg.vector_norm(yt)) / d ** 3 < 1e-4
