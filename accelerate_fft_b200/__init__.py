@@ -138,6 +138,8 @@ class Plan:
             st = L.b200fftPlan2d(ctypes.byref(self.h), dims[0], dims[1], typ)
         elif kind == "3d":
             st = L.b200fftPlan3d(ctypes.byref(self.h), dims[0], dims[1], dims[2], typ)
+        elif kind == "axis":   # dims = (outer, n, inner)
+            st = L.b200fftPlanAxis(ctypes.byref(self.h), dims[0], dims[1], dims[2], typ)
         else:
             raise ValueError(kind)
         _lib.check(st, "plan " + kind)

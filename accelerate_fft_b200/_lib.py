@@ -20,7 +20,7 @@ EXPORTS = [
     "b200fftNumPasses", "b200fftKernelLaunches", "b200fftDescribe",
     "accfft_fft", "accfft_fft1D", "accfft_fft2D", "accfft_fft3D", "accfft_run_host",
     "accfft_set_fused_inverse", "accfft_plan_cache_size", "accfft_plan_cache_clear",
-    "b200fftSlabPlanCreate", "b200fftSlabLocalXY", "b200fftSlabPack", "b200fftSlabUnpackZ",
+    "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack",
 ]
 
 
@@ -80,9 +80,9 @@ def lib():
     L.accfft_set_fused_inverse.argtypes = [i]
     L.accfft_set_fused_inverse.restype = None
     L.accfft_plan_cache_clear.restype = None
-    if hasattr(L, "b200fftSlabPack"):
-        L.b200fftSlabPack.argtypes = [i, vp, vp, i64, i64, i64, i, vp]
-        L.b200fftSlabUnpackZ.argtypes = [i, vp, vp, i64, i64, i64, i, vp]
+    L.b200fftPlanAxis.argtypes = [pvp, i64, i64, i64, i]
+    L.b200fftSlabPack.argtypes = [i, vp, vp, i64, i64, i64, i, vp]
+    L.b200fftSlabUnpack.argtypes = [i, vp, vp, i64, i64, i64, i, vp]
     _lib = L
     return L
 

@@ -21,6 +21,7 @@ struct Geom {
   int tw_div;
   int tw_lo_bits;
   int swap_in, swap_out;         // inverse = swap(fwd(swap(x)))
+  int stream_hint;               // A/B switch: evict-first loads/stores for the bulk data
 };
 
 template <typename T_, int N_, int E_, int TL_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
@@ -155,7 +156,7 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
     const long long step = (long long)K::TPT * g.ins;
     static_for<0, K::E>([&](auto ec) {
       constexpr int e = ec;
-      v[e] = valid ? ld_stream(ip + e * step) : C{0, 0};
+      v[e] = valid ? (g.stream_hint ? ld_stream(ip + e * step) : ip[e * step]) : C{0, 0};
     });
     if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
   }
@@ -179,7 +180,7 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
     if (g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
     C* op = out + (long long)b * g.obs + (long long)o * g.oos + (long long)line * g.ols + (long long)t * g.ons;
     const long long step = (long long)K::TPT * g.ons;
-    if (valid) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; st_stream(op + e * step, v[e]); });
+    if (valid) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; if (g.stream_hint) st_stream(op + e * step, v[e]); else op[e * step] = v[e]; });
   }
 }
 

@@ -352,6 +352,36 @@ cudaError_t launch_copy_scale(int is_double, const void* src, void* dst, long lo
   return cudaGetLastError();
 }
 
+// [dl][h][w] <-> [P][dl][h/P][w]; one 16-byte vector per thread-iteration
+template <typename V, bool PACK>
+__global__ void slab_pack_kernel(const V* __restrict__ src, V* __restrict__ dst, long long dl, long long h, long long wv, int P) {
+  const long long hl = h / P, total = dl * h * wv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long x = idx % wv, y = (idx / wv) % h, z = idx / (wv * h);
+    const long long r = y / hl, yl = y % hl;
+    const long long packed = ((r * dl + z) * hl + yl) * wv + x;
+    if (PACK) dst[packed] = src[idx]; else dst[idx] = src[packed];
+  }
+}
+
+cudaError_t launch_slab_pack(int is_double, bool pack, const void* src, void* dst, long long dl, long long h, long long w, int P,
+                             cudaStream_t stream) {
+  // vector = 16 bytes = 2 c64 or 1 c128
+  const long long wv = is_double ? w : w / 2;
+  const bool vec_ok = is_double || (w % 2 == 0);
+  const long long total = dl * h * (vec_ok ? wv : w);
+  long long b = (total + 255) / 256;
+  unsigned blocks = (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+  if (vec_ok) {
+    if (pack) slab_pack_kernel<float4, true><<<blocks, 256, 0, stream>>>((const float4*)src, (float4*)dst, dl, h, wv, P);
+    else slab_pack_kernel<float4, false><<<blocks, 256, 0, stream>>>((const float4*)src, (float4*)dst, dl, h, wv, P);
+  } else {
+    if (pack) slab_pack_kernel<float2, true><<<blocks, 256, 0, stream>>>((const float2*)src, (float2*)dst, dl, h, w, P);
+    else slab_pack_kernel<float2, false><<<blocks, 256, 0, stream>>>((const float2*)src, (float2*)dst, dl, h, w, P);
+  }
+  return cudaGetLastError();
+}
+
 int generic_set_attrs() {
   if (cudaFuncSetAttribute(mixed_radix_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;

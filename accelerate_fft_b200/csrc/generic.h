@@ -40,6 +40,8 @@ cudaError_t launch_generic(int is_double, const GenericPass& gp, const void* src
                            double scale, cudaStream_t stream, long long* nlaunches);
 cudaError_t launch_copy_scale(int is_double, const void* src, void* dst, long long count, double scale, cudaStream_t stream,
                               long long* nlaunches);
+cudaError_t launch_slab_pack(int is_double, bool pack, const void* src, void* dst, long long dl, long long h, long long w, int P,
+                             cudaStream_t stream);
 int generic_set_attrs();
 
 }  // namespace b200fft

@@ -211,6 +211,7 @@ struct Builder {
     ps.kind = PK_LINES;
     ps.k = k;
     g.ntl = (g.nl + k->TL - 1) / k->TL;
+    { const char* sh = getenv("B200FFT_STREAM_HINT"); g.stream_hint = sh ? atoi(sh) : 0; }
     ps.g = g;
     ps.inplace_ok = inplace_ok;
     ps.tws = make_stage_twiddles(p, k);
@@ -447,6 +448,19 @@ int b200fftPlanMany1d(b200fftHandle* plan, int64_t n, int64_t batch, int type) {
   return finish_plan(p, b, plan);
 }
 
+int b200fftPlanAxis(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner, int type) {
+  if (!plan) return B200FFT_INVALID_VALUE;
+  int dbl;
+  if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
+  if (n < 1 || outer < 1 || inner < 1) return B200FFT_INVALID_SIZE;
+  if (int e = have_device()) return e;
+  auto* p = new b200fft_plan_s;
+  p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = outer * inner; p->total = n * outer * inner;
+  Builder b{p};
+  b.axis(outer, n, inner);
+  return finish_plan(p, b, plan);
+}
+
 int b200fftPlan1d(b200fftHandle* plan, int64_t n, int type, int64_t batch) { return b200fftPlanMany1d(plan, n, batch, type); }
 
 int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type) {
@@ -557,6 +571,23 @@ const char* b200fftErrorString(int s) {
     case B200FFT_NOT_SUPPORTED: return "B200FFT_NOT_SUPPORTED";
     default: return "B200FFT_UNKNOWN_ERROR";
   }
+}
+
+static int slab_pack_common(int type, bool pack, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks,
+                            b200fftStream stream) {
+  int dbl;
+  if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
+  if (!src || !dst || src == dst) return B200FFT_INVALID_VALUE;
+  if (dl < 1 || h < 1 || w < 1 || nranks < 1 || h % nranks) return B200FFT_INVALID_SIZE;
+  if (launch_slab_pack(dbl, pack, src, dst, dl, h, w, nranks, (cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return B200FFT_EXEC_FAILED; }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return B200FFT_SUCCESS;
+}
+int b200fftSlabPack(int type, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks, b200fftStream stream) {
+  return slab_pack_common(type, true, src, dst, dl, h, w, nranks, stream);
+}
+int b200fftSlabUnpack(int type, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks, b200fftStream stream) {
+  return slab_pack_common(type, false, src, dst, dl, h, w, nranks, stream);
 }
 
 size_t b200fftScratchBytes(b200fftHandle p) { return p ? p->scratch_bytes + p->extra_bytes : 0; }

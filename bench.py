@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native FFT hot path (contract in the task brief).
+
+Default workload = BASELINE.json configs[1]: batched 1D complex Double FFT, n=4096, batch=65536,
+one step = Forward then Inverse (normalised) over the whole batch; at N GPUs the batch is sharded
+contiguously across ranks with no data-path collective (strong scaling, as BASELINE.json states).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg1..cfg5] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job GFLOP/s (5 N log2 N per transform) with inputs
+resident in HBM; `e2e` = the same through host buffers (pinned H2D of the step's input, D2H of its
+result inside the timed region); `roofline` = algorithmic bytes / measured launch time of the
+dominant kernel against the measured HBM copy bandwidth; `cpu_baseline` = the oracle port of the
+reference's pure-Accelerate path (oracle/, C) on the box's host cores, bounded sample.
+--impl reference times that CPU path alone (the reference's GPU/CPU bindings need GHC+cuFFT/FFTW,
+which this image does not have).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (kind, dims, dtype, batch, min passes, description)
+    "cfg1": ("fft", (1024,), "c64", 4096, 1, "1D c64 n=1024 batch=4096 Forward"),
+    "cfg2": ("fft", (4096,), "c128", 65536, 1, "batched 1D c128 n=4096 batch=65536 Forward+Inverse"),
+    "cfg3": ("fft2D", (8192, 8192), "c64", 1, 2, "2D c64 8192x8192 Forward"),
+    "cfg4": ("fft1D", (1 << 28,), "c64", 1, 2, "1D c64 n=2^28 Forward (four-step)"),
+    "cfg5": ("fft3D", (1024, 1024, 1024), "c64", 1, 3, "3D c64 1024^3 Forward"),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(cfg):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(cfg)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                c, m, pw = float(r[0]), float(r[1]), float(r[2])
+            except Exception:
+                continue
+            mx = m
+            if c >= 0.5 * m:   # under load (idle parks at ~120 MHz)
+                sm.append(c)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            sm = [float(r[0]) for r in rows if r and r[0].strip().replace(".", "").isdigit()]
+        out["sm_mhz"] = statistics.median(sm) if sm else None
+        out["sm_max_mhz"] = mx
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(rows)
+        return out
+
+
+def flops_of(cfg, batch):
+    kind, dims, dt, _, _, _ = CONFIGS[cfg]
+    npts = 1
+    for d in dims:
+        npts *= d
+    per = 5.0 * npts * math.log2(npts) * batch
+    return per * (2 if cfg == "cfg2" else 1)      # cfg2's step is Forward + Inverse
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------------
+def cpu_step(cfg, sample_batch, threads, np, oracle, x):
+    kind, dims, dt, _, _, _ = CONFIGS[cfg]
+    if cfg == "cfg2":
+        y = oracle.fft("Forward", x, threads=threads)
+        return oracle.fft("Inverse", y, threads=threads)
+    return getattr(oracle, kind)("Forward", x, threads=threads)
+
+
+def cpu_sample(cfg, np):
+    """A bounded sample of the workload (same shape per transform, fewer transforms)."""
+    kind, dims, dt, batch, _, _ = CONFIGS[cfg]
+    dtype = np.complex64 if dt == "c64" else np.complex128
+    rng = np.random.default_rng(1000 + int(cfg[3]))
+    if cfg == "cfg1":
+        shape, sb, what = (4096, 1024), 4096, "the whole workload (4096 rows)"
+    elif cfg == "cfg2":
+        shape, sb, what = (4096, 4096), 4096, "4096 of the 65536 rows (1/16 of the batch), Forward+Inverse"
+    elif cfg == "cfg3":
+        shape, sb, what = (2048, 2048), 1.0 / 16, "a 2048x2048 fft2D (1/16 of the points; GFLOP/s by its own 5NlogN)"
+    elif cfg == "cfg4":
+        shape, sb, what = (1 << 24,), 1.0 / 16, "a 2^24-point fft1D (1/16 of the points; GFLOP/s by its own 5NlogN)"
+    else:
+        shape, sb, what = (256, 256, 256), 1.0 / 64, "a 256^3 fft3D (1/64 of the points; GFLOP/s by its own 5NlogN)"
+    x = (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(dtype)
+    if cfg in ("cfg1", "cfg2"):
+        fl = flops_of(cfg, sb)
+    else:
+        npts = x.size
+        fl = 5.0 * npts * math.log2(npts)
+    return x, fl, what
+
+
+def run_cpu_baseline(cfg, steps=1, warmup=0):
+    import numpy as np
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    x, fl, what = cpu_sample(cfg, np)
+    for _ in range(warmup):
+        cpu_step(cfg, None, threads, np, oracle, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(cfg, None, threads, np, oracle, x)
+    dt = (time.perf_counter() - t0) / steps
+    out = {"value": fl / dt / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+           "sample": what + "; oracle/ C port of Adhoc.hs (pure-Accelerate path), OpenMP over rows", "ms_per_step": dt * 1e3}
+    # FFTW-class stand-in for the reference's llvm-cpu path (FFTW itself is not in the image)
+    try:
+        import scipy.fft as sf
+        kind = CONFIGS[cfg][0]
+        f = {"fft": lambda a: sf.fft(a, axis=-1, workers=threads), "fft1D": lambda a: sf.fft(a, workers=threads),
+             "fft2D": lambda a: sf.fft2(a, workers=threads), "fft3D": lambda a: sf.fftn(a, workers=threads)}[kind]
+        f(x)
+        t0 = time.perf_counter()
+        y = f(x)
+        if cfg == "cfg2":
+            sf.ifft(y, axis=-1, workers=threads)
+        d2 = time.perf_counter() - t0
+        out["fftw_standin"] = {"impl": "scipy.fft (pocketfft)", "value": fl / d2 / 1e9, "unit": "GFLOP/s", "cores": threads}
+    except Exception:
+        pass
+    return out, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = args.config
+    base, dt = run_cpu_baseline(cfg, steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    kind, dims, dtp, batch, _, desc = CONFIGS[cfg]
+    line = {
+        "impl": "reference", "metric": "fft_gflops_5nlog2n", "value": base["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64" if dtp == "c128" else "f32", "data": "synthetic",
+        "config": {"workload": desc, "sample": base["sample"]},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference's own bindings need GHC + FFTW/cuFFT (absent here): this arm is the oracle port of its pure-Accelerate CPU path",
+    }
+    if "fftw_standin" in base:
+        line["fftw_standin"] = base["fftw_standin"]
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main_gpu(args):
+    import torch
+    import accelerate_fft_b200 as af
+    af.lib()   # fail loudly if the extension is missing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
+
+    # clocks are sampled from before the warm-up until after the launch-time measurement (the timed
+    # region itself can be shorter than one nvidia-smi period)
+    sampler = ClockSampler(local) if rank == 0 else None
+    cfg = args.config
+    kind, dims, dtp, batch, min_passes, desc = CONFIGS[cfg]
+    dt = torch.complex64 if dtp == "c64" else torch.complex128
+    esz = 8 if dtp == "c64" else 16
+    if cfg == "cfg5" and world > 1:
+        from accelerate_fft_b200 import slab
+        return slab.bench_slab(args, af, dist, rank, local, world, desc, measured_peak, ClockSampler)
+    if cfg in ("cfg3", "cfg4", "cfg5") and world > 1:
+        # BASELINE.json names these single-GPU: replicas only (DESIGN.md section "multi-GPU")
+        replicas, my_batch, scaling = world, 1, "weak"
+    else:
+        if batch % world:
+            raise SystemExit("batch %d not divisible by %d ranks" % (batch, world))
+        replicas, my_batch, scaling = 1, batch // world, "strong"
+
+    shape = ((my_batch,) + dims) if kind == "fft" else dims
+    n_local = 1
+    for s in shape:
+        n_local *= s
+    torch.manual_seed(1000 + int(cfg[3]) + 7919 * rank)
+    # several distinct buffer pairs when one fits in L2 (cfg1): rotate so every step streams from HBM
+    nbytes = n_local * esz
+    nbuf = 1 if nbytes * 2 > 4 * 126e6 else int(math.ceil(4 * 126e6 / (2 * nbytes)))
+    xs = [torch.view_as_complex(torch.rand(shape + (2,), dtype=torch.float32 if dtp == "c64" else torch.float64, device="cuda") * 2 - 1)
+          for _ in range(nbuf)]
+    af.set_fused_inverse(True)   # 1/n folded into the last butterfly pass (same result as FFT.hs:83's extra map)
+    f = getattr(af, kind)
+
+    def step(i):
+        x = xs[i % nbuf]
+        if cfg == "cfg2":
+            return f("Inverse", f("Forward", x))
+        return f("Forward", x)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        y = step(i)
+    del y
+    barrier()
+
+    # ---- device-resident timing: K steps, CUDA events, max over ranks -------------------------
+    l0 = af.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        y = step(i)
+    ev1.record()
+    barrier()
+    launches = af.kernel_launches() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    del y
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    total_flops = flops_of(cfg, batch if kind == "fft" else 1) * replicas
+    value = total_flops / (ms_step * 1e-3) / 1e9
+
+    # ---- dominant-kernel launch time (events around single launches, same stream) --------------
+    plan_kind = {"fft": "many", "fft1D": "1d", "fft2D": "2d", "fft3D": "3d"}[kind]
+    plan = af.Plan(plan_kind, list(dims), af.C2C if dtp == "c64" else af.Z2Z, my_batch if kind == "fft" else 1)
+    npass = plan.num_passes
+    out = torch.empty_like(xs[0])
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2 * 8)]
+    for _ in range(2):
+        plan.exec(xs[0], out, af.FORWARD)
+    torch.cuda.synchronize()
+    samples = []
+    t_end = time.perf_counter() + 0.6          # keep the GPU loaded long enough for the clock sampler
+    while True:
+        for i in range(8):
+            e[2 * i].record()
+            plan.exec(xs[i % nbuf], out, af.FORWARD)
+            e[2 * i + 1].record()
+        torch.cuda.synchronize()
+        samples += [e[2 * i].elapsed_time(e[2 * i + 1]) for i in range(8)]
+        if time.perf_counter() > t_end:
+            break
+    exec_ms = statistics.mean(samples)
+    clocks = sampler.stop() if sampler else None
+    plan_desc = plan.describe().strip().split("\n")
+    plan.destroy()
+    del out
+    peak, peak_src = measured_peak()
+    alg_bytes = min_passes * 2 * nbytes              # min passes x 2 x N_total x sizeof(complex)
+    achieved = alg_bytes / (exec_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(cfg), "peak_source": peak_src,
+                "kernel": "fft_lines_kernel (%d launch(es) per transform direction; algorithmic passes %d)" % (npass, min_passes),
+                "algorithmic_bytes_per_exec": alg_bytes, "exec_ms": exec_ms,
+                "per_pass_frac": (npass * 2 * nbytes) / (exec_ms * 1e-3) / 1e9 / peak, "plan": plan_desc}
+
+    # ---- end to end through host buffers (pinned H2D of the input, D2H of the result) ----------
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(shape, dtype=dt).pin_memory()
+        hx.copy_(xs[0].cpu())
+        hy = torch.empty(shape, dtype=dt).pin_memory()
+        dx = torch.empty_like(xs[0])
+        ksteps = max(1, min(args.steps, 3 if nbytes > 1e9 else args.steps))
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True)
+            if cfg == "cfg2":
+                r = f("Inverse", f("Forward", dx))
+            else:
+                r = f("Forward", dx)
+            hy.copy_(r, non_blocking=True)
+        e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(ksteps):
+            e2e_step()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / ksteps
+        e2e = {"value": total_flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms, "steps": ksteps,
+               "api": "accelerate_fft_b200.%s on a device copy of pinned host buffers (accfft_* C ABI underneath)" % kind}
+        del hx, hy, dx
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = run_cpu_baseline(cfg)
+
+    if rank == 0:
+        line = {
+            "metric": "fft_gflops_5nlog2n", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64" if dtp == "c128" else "f32", "data": "synthetic",
+            "config": {"workload": desc, "per_gpu_shape": list(shape), "sharding": "batch rows split contiguously across ranks, no collective" if replicas == 1 else "independent replicas",
+                       "l2": "inputs larger than L2 (%.0f MB per buffer x %d rotating buffers)" % (nbytes / 1e6, nbuf),
+                       "inverse_scale": "fused into the last pass", "step": "Forward+Inverse" if cfg == "cfg2" else "Forward"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "hbm_gbs_whole_step": (2 if cfg == "cfg2" else 1) * alg_bytes * world / (ms_step * 1e-3) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

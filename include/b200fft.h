@@ -58,6 +58,10 @@ int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type
 /* FFT.planMany [n] Nothing Nothing t batch (rank 1, contiguous, idist = odist = n) -- PTX.hs:162,169 */
 int b200fftPlanMany1d(b200fftHandle* plan, int64_t n, int64_t batch, int type);
 
+/* One axis of a dense array viewed as [outer][n][inner] (inner = element stride of the transformed axis).
+ * Building block of the slab-decomposed multi-GPU 3D transform; no reference call site. */
+int b200fftPlanAxis(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner, int type);
+
 /* FFT.setStream + FFT.execC2C / FFT.execZ2Z  -- PTX.hs:119-124.
  * direction: B200FFT_FORWARD or B200FFT_INVERSE; the element type is baked into the plan. */
 int b200fftExec(b200fftHandle plan, const void* in, void* out, int direction, b200fftStream stream);
@@ -77,6 +81,12 @@ int b200fftNumPasses(b200fftHandle plan);            /* kernel launches (= HBM p
 int64_t b200fftKernelLaunches(void);                 /* process-wide count of kernels launched */
 /* fills `buf` with a one-line-per-pass description of the plan; returns bytes written */
 int b200fftDescribe(b200fftHandle plan, char* buf, int buflen);
+
+/* Slab-decomposed 3D FFT across the GPUs of one box (new capability, the reference is
+ * single-device).  Rank g owns z-planes [g*D/P,(g+1)*D/P).  Pack re-orders a local [dl][h][w] slab into P
+ * contiguous peer blocks [P][dl][h/P][w] for the all-to-all; Unpack is its inverse. */
+int b200fftSlabPack(int type, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks, b200fftStream stream);
+int b200fftSlabUnpack(int type, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks, b200fftStream stream);
 
 /*
  * Host-side mirror of the reference's public API for this path (FFT.hs:63-173 + PTX.hs +
