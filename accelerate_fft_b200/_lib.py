@@ -20,7 +20,7 @@ EXPORTS = [
     "b200fftNumPasses", "b200fftKernelLaunches", "b200fftDescribe",
     "accfft_fft", "accfft_fft1D", "accfft_fft2D", "accfft_fft3D", "accfft_run_host",
     "accfft_set_fused_inverse", "accfft_plan_cache_size", "accfft_plan_cache_clear",
-    "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack",
+    "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack", "b200fftTrimScratch",
 ]
 
 

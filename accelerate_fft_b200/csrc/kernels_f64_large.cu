@@ -8,6 +8,7 @@ void register_f64_large(void (*add)(const KernelEntry&)) {
   REG_ROW(double, 4096, 16, 1, 2, 16, 16, 16);        // v0: 256 thr x 128 regs, 2 CTA/SM  82.2 %
   REG_ROW(double, 4096, 8, 1, 2, 8, 8, 8, 8);         // v1: 512 thr x 64 regs, 2 CTA/SM   76.2 %
   REG_ROW(double, 4096, 8, 1, 1, 8, 8, 8, 8);         // v2: 512 thr x 114 regs, 1 CTA/SM  56.3 %
+  // (tried: minb=3 -> 80 regs, 776 B spills: 43 % -- removed)
   REG_ROW(double, 8192, 16, 1, 0, 16, 16, 16, 2);
 }
 }  // namespace b200fft

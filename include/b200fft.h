@@ -75,6 +75,10 @@ int b200fftDestroy(b200fftHandle plan);
 
 const char* b200fftErrorString(int status);
 
+/* Per-exec scratch of multi-pass plans is stream-ordered and comes from a library-owned memory pool that
+ * keeps its pages between execs; this returns them to the driver (no reference counterpart). */
+int b200fftTrimScratch(void);
+
 /* Introspection used by the bench / tests (no reference counterpart). */
 size_t b200fftScratchBytes(b200fftHandle plan);      /* stream-ordered scratch one exec allocates */
 int b200fftNumPasses(b200fftHandle plan);            /* kernel launches (= HBM passes) per exec */
