@@ -21,6 +21,9 @@ KernelEntry make_entry() {
   return e;
 }
 
+template <class R>
+KernelEntry make_ring_entry();
+
 #define REG_ROW(...)   add(make_entry<Cfg<__VA_ARGS__>, false, false, false>())
 #define REG_COL(...)   add(make_entry<Cfg<__VA_ARGS__>, true, true, false>()); add(make_entry<Cfg<__VA_ARGS__>, true, true, true>())
 #define REG_TRANS(...) add(make_entry<Cfg<__VA_ARGS__>, false, true, false>())

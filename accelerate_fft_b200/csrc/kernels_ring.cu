@@ -1,0 +1,34 @@
+// Persistent TMA-fed row kernels (ring_kernel.cuh) for the tile sizes where occupancy alone cannot
+// hide HBM latency.          RingCfg<Cfg<T, N, E, TL, minb, R0, R1, R2, R3>, G groups, NS stages>
+#include "kernel_inst.cuh"
+#include "ring_kernel.cuh"
+namespace b200fft {
+
+template <class R>
+KernelEntry make_ring_entry() {
+  using K = typename R::Base;
+  KernelEntry e{};
+  e.is_double = sizeof(typename K::real) == 8;
+  e.N = K::N; e.E = K::E; e.TL = K::TL;
+  e.S = K::S;
+  for (int i = 0; i < 4; i++) e.rad[i] = K::rad[i];
+  e.tw_len = K::TW_LEN;
+  e.flavor = FL_RING;
+  e.threads = R::THREADS;
+  e.smem = R::SMEM;
+  e.G = R::G; e.NS = R::NS;
+  e.minb = 1;
+  e.func = reinterpret_cast<const void*>(&fft_ring_rows_kernel<R>);
+  return e;
+}
+
+#define REG_RING(G, NS, ...) add(make_ring_entry<RingCfg<Cfg<__VA_ARGS__>, G, NS>>())
+
+void register_ring(void (*add)(const KernelEntry&)) {
+  REG_RING(2, 3, double, 4096, 16, 1, 1, 16, 16, 16);    // cfg2: 2 groups x 256 thr, 3 x 68 KB stages
+  // measured on B200 (profiles/r01_ring_vs_plain.txt): the ring wins only where FP64 + 68 KB tiles leave the plain
+  // kernel latency-bound (c128 N=4096: 81.7 % -> 88.4 % of measured HBM peak).  It loses for c128 N=2048
+  // (93.0 % vs 96.3 %), c64 N=8192 (73.5 % vs 80.4 %) and c64 N=4096 (81.3 % vs 91.6 %), where the extra
+  // shared-memory traffic of the staged tile costs more than the hidden latency gains -- not instantiated.
+}
+}  // namespace b200fft

@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +46,7 @@ static void ensure_registry() {
     register_f64_small(add_entry);
     register_f64_large(add_entry);
     register_f64_col(add_entry);
+    register_ring(add_entry);
   });
 }
 
@@ -123,6 +125,8 @@ enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3 };
 struct Pass {
   int kind = PK_LINES;
   const KernelEntry* k = nullptr;  // PK_LINES
+  const KernelEntry* ring = nullptr;  // PK_LINES rows: persistent TMA-fed alternative (needs 16-byte aligned buffers)
+  int ring_ntl = 0, ring_grid = 0;
   Geom g{};
   GenericPass gp{};                // PK_GENERIC / PK_BLUESTEIN
   bool inplace_ok = false;         // reads and writes the same positions tile by tile
@@ -252,6 +256,17 @@ struct Builder {
              k->variant, k->E, k->TL, k->minb, flavor == FL_ROW ? "row" : flavor == FL_COL ? "col" : "trans", tw4 ? "+tw" : "", k->rad[0], k->rad[1],
              k->rad[2], k->rad[3], k->threads, k->smem, ps.ntiles);
     ps.desc = buf;
+    if (flavor == FL_ROW && !tw4 && g.ils == N && g.ols == N && g.ins == 1 && g.ons == 1 && g.nb == 1 && g.no == 1 &&
+        !(getenv("B200FFT_NO_RING") && atoi(getenv("B200FFT_NO_RING")))) {
+      const KernelEntry* r = find_kernel(p->is_double, N, FL_RING, 0, 0);
+      // worth it only when every SM gets a few tiles to pipeline
+      if (r && (g.nl + r->TL - 1) / r->TL >= 2LL * 148) {
+        ps.ring = r;
+        ps.ring_ntl = (g.nl + r->TL - 1) / r->TL;
+        snprintf(buf, sizeof buf, " | ring: G=%d NS=%d threads=%d smem=%zu tiles=%d", r->G, r->NS, r->threads, r->smem, ps.ring_ntl);
+        ps.desc += buf;
+      }
+    }
     push(ps);
     return true;
   }
@@ -420,11 +435,20 @@ struct Builder {
   }
 };
 
-static int set_func_attrs(const b200fft_plan_s* p) {
-  for (const auto& ps : p->passes) {
+static int set_func_attrs(b200fft_plan_s* p) {
+  for (auto& ps : p->passes) {
     if (ps.kind == PK_LINES && ps.k->smem > 48 * 1024) {
       if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess)
         return B200FFT_INTERNAL_ERROR;
+    }
+    if (ps.kind == PK_LINES && ps.ring) {
+      int dev = 0, nsm = 0, occ = 0;
+      bool ok = cudaFuncSetAttribute(ps.ring->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.ring->smem) == cudaSuccess &&
+                cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.ring->func, ps.ring->threads, ps.ring->smem) == cudaSuccess && occ > 0;
+      if (!ok) { cudaGetLastError(); ps.ring = nullptr; continue; }   // the plain kernel still serves the pass
+      long long grid = (long long)nsm * occ;
+      ps.ring_grid = (int)(grid < ps.ring_ntl ? grid : ps.ring_ntl);
     }
   }
   return generic_set_attrs();
@@ -552,7 +576,12 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
       double scd = sc;
       void* args[] = {&g, (void*)&src, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
                       p->is_double ? (void*)&scd : (void*)&scf};
-      ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
+      if (ps.ring && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        g.ntl = ps.ring_ntl;
+        ce = cudaLaunchKernel(ps.ring->func, dim3((unsigned)ps.ring_grid), dim3(ps.ring->threads), args, ps.ring->smem, stream);
+      } else {
+        ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
+      }
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (ps.kind == PK_COPY) {
       long long nl = 0;

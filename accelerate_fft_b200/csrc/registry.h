@@ -5,7 +5,7 @@
 
 namespace b200fft {
 
-enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2 };
+enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3 };  // FL_RING: persistent TMA-fed rows (ring_kernel.cuh)
 
 struct KernelEntry {
   int is_double;
@@ -17,6 +17,7 @@ struct KernelEntry {
   size_t smem;
   int S, rad[4];
   int tw_len;      // stage twiddle table length (complex elements)
+  int G, NS;       // FL_RING: thread groups per CTA, stage buffers
   const void* func;
 };
 
@@ -32,5 +33,6 @@ void register_f32_col(void (*add)(const KernelEntry&));
 void register_f64_small(void (*add)(const KernelEntry&));
 void register_f64_large(void (*add)(const KernelEntry&));
 void register_f64_col(void (*add)(const KernelEntry&));
+void register_ring(void (*add)(const KernelEntry&));
 
 }  // namespace b200fft

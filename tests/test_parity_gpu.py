@@ -72,6 +72,35 @@ def test_fft_pow2_vs_oracle(af, oracle, dtype, mode):
             assert rel_l2(y[:1], ex.astype(np.complex128)) <= bar(dtype, n) / 2, (n, mode)
 
 
+@pytest.mark.parametrize("n,dtype", [(4096, np.complex128)])
+@pytest.mark.parametrize("mode", ["Forward", "Inverse"])
+def test_persistent_tma_row_kernel_vs_oracle(af, oracle, n, dtype, mode):
+    """Batches large enough (>= 2 tiles per SM) take the persistent TMA-fed ring kernel (ring_kernel.cuh);
+    an odd batch exercises uneven tile counts per CTA; with the ring disabled the plan falls back to the
+    plain kernel with the same result."""
+    import torch
+    rng = np.random.default_rng(21)
+    batch = 2 * 148 * 3 + 5
+    x = rand_complex(rng, (batch, n), dtype)
+    p = af.Plan("many", [n], af.C2C if dtype == np.complex64 else af.Z2Z, batch)
+    assert "ring" in p.describe()
+    p.destroy()
+    y = gpu(af, "fft", mode, x)
+    ref = oracle.fft(mode, x, threads=8)
+    assert rel_l2(y, ref) <= bar(dtype, n)
+    worst = max(rel_l2(y[i], ref[i]) for i in (0, 1, 147, 148, 295, 296, batch - 2, batch - 1))
+    assert worst <= bar(dtype, n)
+    # the same rows through the plain (non-persistent) kernel must agree bit for bit
+    os.environ["B200FFT_NO_RING"] = "1"
+    try:
+        af.lib().accfft_plan_cache_clear()
+        y2 = gpu(af, "fft", mode, x)
+    finally:
+        os.environ["B200FFT_NO_RING"] = "0"
+        af.lib().accfft_plan_cache_clear()
+    assert np.array_equal(y, y2)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_fft_every_length_1_to_130_and_reference_range(af, oracle, dtype):
     """cuFFT accepts every length; the reference's PTX suite draws n in [1,1024] (test/Test/Base.hs:44-45)."""

@@ -69,3 +69,8 @@ if which == "var":
     for v in range(4):
         withvar(f"c1024f={v}", lambda: bench(f"cfg5 1024^3 col v{v}", "3d", [1024, 1024, 1024], af.C2C, 1, 3, 3))
     bench("cfg1 c64 n=1024 b=4096", "many", [1024], af.C2C, 4096, 1, 50)
+if which == "ring":
+    bench("cfg2 c128 n=4096 b=65536", "many", [4096], af.Z2Z, 65536, 1, 10)
+    bench("c128 n=2048 b=32768", "many", [2048], af.Z2Z, 32768, 1, 10)
+    bench("c64 n=8192 b=16384", "many", [8192], af.C2C, 16384, 1, 10)
+    bench("c64 n=4096 b=32768", "many", [4096], af.C2C, 32768, 1, 10)
