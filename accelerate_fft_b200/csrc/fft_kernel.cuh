@@ -19,9 +19,9 @@ struct Geom {
   int nb, no, nl, ntl;           // ntl = ceil(nl / TL)
   // four-step twiddle  w_L^(k * (line / tw_div)),  L = 2^(tw_hi_bits_total): exponent split lo/hi
   int tw_div;
+  int tw_from_o;                 // four-step multiplier is the outer index o instead of line / tw_div
   int tw_lo_bits;
-  int swap_in, swap_out;         // inverse = swap(fwd(swap(x)))
-  int stream_hint;               // A/B switch: evict-first loads/stores for the bulk data
+  int swap_in, swap_out;         // conjugate on load / on store: inverse = conj(fwd(conj(x)))
 };
 
 template <typename T_, int N_, int E_, int TL_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
@@ -60,26 +60,38 @@ struct Cfg {
   }
 };
 
+// Shared-memory address of point i of line l.  Every index used below splits as i = it + ic with `it` a
+// function of the thread and `ic` a compile-time constant chosen so that the low LOGQ bits never carry
+// (all of N, E, TL, TPT, the radices and Q = 2^LOGQ are powers of two), hence
+//     addr(l, it + ic) = addr_rt(l, it) + addr_ct(ic)
+// and each access is one runtime base (computed once per stage) plus an immediate offset -- the
+// integer/address instructions were 38 % of the issue slots before this split (profiles/r01_sass_mix_*.txt).
 template <class K, bool COL>
-__device__ __forceinline__ int smem_addr(int l, int i) {
-  if constexpr (COL) return i * K::TL + (i >> K::LOGQ) * K::XPAD + l;
-  else return l * K::PITCH + i + (i >> K::LOGQ);
+__device__ __forceinline__ int addr_rt(int l, int it) {
+  if constexpr (COL) return it * K::TL + (it >> K::LOGQ) * K::XPAD + l;
+  else return l * K::PITCH + it + (it >> K::LOGQ);
+}
+template <class K, bool COL>
+__device__ __forceinline__ constexpr int addr_ct(int ic) {
+  if constexpr (COL) return ic * K::TL + (ic >> K::LOGQ) * K::XPAD;
+  else return ic + (ic >> K::LOGQ);
 }
 
 // One register stage: E/R butterflies of radix R per thread.
 template <class K, int s, typename C>
 __device__ __forceinline__ void run_stage(C (&v)[K::E], int t, const C* __restrict__ tws) {
   constexpr int R = K::rad[s], B = K::E / R, Ns = K::ns(s);
+  // twiddle index k = (t + b*TPT) & (Ns-1): thread part + compile-time part
+  const C* tp0 = tws + K::tw_off(s) + ((Ns <= K::TPT) ? (t & (Ns - 1)) : t);
   static_for<0, B>([&](auto bc) {
     constexpr int b = bc;
     C a[R];
     static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r] = v[b + r * B]; });
     if constexpr (s > 0) {
-      const int k = (t + b * K::TPT) & (Ns - 1);
-      const C* tp = tws + K::tw_off(s) + k;
+      constexpr int kc = (Ns <= K::TPT) ? 0 : ((b * K::TPT) & (Ns - 1));
       static_for<1, R>([&](auto rc) {
         constexpr int r = rc;
-        a[r] = cmul(a[r], __ldg(tp + (r - 1) * Ns));
+        a[r] = cmul(a[r], __ldg(tp0 + kc + (r - 1) * Ns));
       });
     }
     dft<R>(a);
@@ -87,101 +99,170 @@ __device__ __forceinline__ void run_stage(C (&v)[K::E], int t, const C* __restri
   });
 }
 
-// Stockham scatter of stage s results into shared memory.
+// Stockham scatter of stage s results into shared memory: butterfly j = t + b*TPT writes its q-th output to
+// point (j & ~(Ns-1))*R + (j & (Ns-1)) + q*Ns.
 template <class K, int s, bool COL, typename C>
 __device__ __forceinline__ void scatter(const C (&v)[K::E], C* sm, int l, int t) {
   constexpr int R = K::rad[s], B = K::E / R, Ns = K::ns(s);
+  constexpr bool SMALL = Ns <= K::TPT;
+  const int it = SMALL ? (t & ~(Ns - 1)) * R + (t & (Ns - 1)) : t;
+  C* base = sm + addr_rt<K, COL>(l, it);
   static_for<0, B>([&](auto bc) {
     constexpr int b = bc;
-    const int j = t + b * K::TPT;
-    const int base = (j & ~(Ns - 1)) * R + (j & (Ns - 1));
+    constexpr int jb = b * K::TPT;
+    constexpr int ic0 = SMALL ? jb * R : (jb & ~(Ns - 1)) * R + (jb & (Ns - 1));
     static_for<0, R>([&](auto qc) {
       constexpr int q = qc;
-      sm[smem_addr<K, COL>(l, base + q * Ns)] = v[b + q * B];
+      base[addr_ct<K, COL>(ic0 + q * Ns)] = v[b + q * B];
     });
   });
 }
 
 template <class K, bool COL, typename C>
 __device__ __forceinline__ void gather(C (&v)[K::E], const C* sm, int l, int t) {
-  static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = sm[smem_addr<K, COL>(l, t + e * K::TPT)]; });
+  const C* base = sm + addr_rt<K, COL>(l, t);
+  static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = base[addr_ct<K, COL>(e * K::TPT)]; });
 }
 
-template <class K, int s, bool LLF, bool SLF, typename C>
-__device__ __forceinline__ void stages(C (&v)[K::E], C* sm, int& l, int& t, const C* __restrict__ tws) {
-  // the shared-memory layout is columnar only when both ends are line-fastest
-  constexpr bool COL = LLF && SLF;
-  run_stage<K, s>(v, t, tws);
-  if constexpr (s + 1 < K::S) {
-    if constexpr (s > 0) __syncthreads();  // readers of the previous exchange are done
-    scatter<K, s, COL>(v, sm, l, t);
-    __syncthreads();
-    if constexpr (s + 2 == K::S && LLF != SLF) {  // switch to the store mapping for the last stage
-      const int tid = threadIdx.x;
-      if constexpr (SLF) { l = tid % K::TL; t = tid / K::TL; } else { t = tid % K::TPT; l = tid / K::TPT; }
-    }
-    gather<K, COL>(v, sm, l, t);
-    stages<K, s + 1, LLF, SLF>(v, sm, l, t, tws);
-  }
-}
+// The inverse direction re-uses the forward butterflies: IDFT(x) = conj(DFT(conj(x))).  The conjugations are
+// applied by the first pass of a plan on load and by the last pass on store; each is compiled as a CLONE of
+// the adjoining code (first stage / last stage) under a warp-uniform branch, so the negation folds into the
+// operand modifiers of the butterflies' FADD/FFMA and costs nothing -- a runtime swap or sign multiply cost
+// 2-4 register moves per point (profiles/r01_sass_mix_*.txt).
 
-// LLF: load mapping is line-fastest (adjacent threads = adjacent lines; use when ils == 1)
-// SLF: same for the store side (ols == 1).   TW4: multiply the result by the four-step twiddle.
-template <class K, bool LLF, bool SLF, bool TW4>
-__global__ void __launch_bounds__(K::THREADS, K::MINB)
-fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
-                 const cpx_t<typename K::real>* __restrict__ tws, const cpx_t<typename K::real>* __restrict__ tw_lo,
-                 const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale) {
+// LLF: load mapping is line-fastest (adjacent threads = adjacent lines; use when ils == 1); otherwise the
+//      points of a line are contiguous (ins == 1, compile-time offsets).
+// SLF: same for the store side (ols == 1, otherwise ons == 1).
+// TW4: multiply the result by the four-step twiddle.
+// CG:  read the input with ld.global.cg (L2 only) -- for tiles another CTA of the SAME launch produced.
+// HINT: bit 0 evict-first loads (ld.global.cs), bit 1 evict-first stores (compile-time: no dead twins).
+//
+// Four-step twiddle w_L^(k*m), k = t + e*TPT the output index held by this thread, m the line's multiplier
+// (line / tw_div, or the outer index o when g.tw_from_o).  Looking every factor up costs two dependent
+// table reads per point (measured: the +tw passes of cfg4 ran at 2.8-4.7 TB/s against 5.5 without);
+// instead one anchor per 8 points comes from the two-level table and the 7 in between from a running
+// product with the step w_L^(TPT*m): 2 + E/4 table reads per thread instead of 2E, error <= 8 ulp.
+template <class K, bool LLF, bool SLF, bool TW4, bool CG = false, int HINT = 0>
+__device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, const cpx_t<typename K::real>* __restrict__ in,
+                                               cpx_t<typename K::real>* __restrict__ out, const cpx_t<typename K::real>* __restrict__ tws,
+                                               const cpx_t<typename K::real>* __restrict__ tw_lo,
+                                               const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale,
+                                               cpx_t<typename K::real>* sm) {
   using T = typename K::real;
   using C = cpx_t<T>;
   static_assert(LLF == SLF || K::S >= 2, "the transposing variant needs an exchange to re-map threads");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  C* sm = reinterpret_cast<C*>(smem_raw);
-
+  constexpr bool COL = LLF && SLF;   // the shared-memory layout is columnar only when both ends are line-fastest
   const int tid = threadIdx.x;
-  const unsigned tile = blockIdx.x;
-  const int lt = tile % (unsigned)g.ntl;
-  const unsigned rest = tile / (unsigned)g.ntl;
-  const int o = rest % (unsigned)g.no;
-  const int b = rest / (unsigned)g.no;
+  int lt, o, b;
+  if (g.no == 1 && g.nb == 1) { lt = (int)tile; o = 0; b = 0; }   // the common shape: no integer divisions
+  else {
+    lt = tile % (unsigned)g.ntl;
+    const unsigned rest = tile / (unsigned)g.ntl;
+    o = rest % (unsigned)g.no;
+    b = rest / (unsigned)g.no;
+  }
 
   int l, t;
   if constexpr (LLF) { l = tid % K::TL; t = tid / K::TL; } else { t = tid % K::TPT; l = tid / K::TPT; }
 
   C v[K::E];
   {
-    const int line = lt * K::TL + l;
-    const bool valid = line < g.nl;
-    const C* ip = in + (long long)b * g.ibs + (long long)o * g.ios + (long long)line * g.ils + (long long)t * g.ins;
-    const long long step = (long long)K::TPT * g.ins;
-    static_for<0, K::E>([&](auto ec) {
-      constexpr int e = ec;
-      v[e] = valid ? (g.stream_hint ? ld_stream(ip + e * step) : ip[e * step]) : C{0, 0};
-    });
-    if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
+    // lines past the end of a ragged last tile re-read the last valid line (no predicates, no zero fill);
+    // their results are simply not stored
+    const int line = min(lt * K::TL + l, g.nl - 1);
+    const C* ip = in + (long long)b * g.ibs + (long long)o * g.ios + (long long)line * g.ils;
+    if constexpr (LLF) ip += (long long)t * g.ins; else ip += t;
+    // byte stride between a thread's points, 32 bits (the planner rejects strides beyond 4 GiB): the address of
+    // point e is ONE IMAD.WIDE.U32 (e * step + base) instead of a 64 x 64-bit multiply-add
+    const unsigned step_b = (unsigned)((long long)K::TPT * g.ins * (long long)sizeof(C));
+    auto head = [&](auto cj) {   // load + first register stage (+ its scatter), cloned on the conjugation
+      constexpr bool CJ = decltype(cj)::value;
+      const char* p = reinterpret_cast<const char*>(ip);
+      static_for<0, K::E>([&](auto ec) {
+        constexpr int e = ec;
+        const C* q = LLF ? reinterpret_cast<const C*>(p + (unsigned long long)(unsigned)e * step_b) : ip + e * K::TPT;
+        C x;
+        if constexpr (CG) x = __ldcg(q);
+        else if constexpr (HINT & 1) x = ld_stream(q);
+        else x = *q;
+        if constexpr (CJ) x.y = -x.y;
+        v[e] = x;
+      });
+      run_stage<K, 0>(v, t, tws);
+      if constexpr (K::S > 1) scatter<K, 0, COL>(v, sm, l, t);
+    };
+    if (g.swap_in) head(std::true_type{}); else head(std::false_type{});
   }
 
-  stages<K, 0, LLF, SLF>(v, sm, l, t, tws);
+  // middle stages: gather, butterflies, scatter
+  static_for<1, (K::S > 1 ? K::S - 1 : 1)>([&](auto sc) {
+    constexpr int s = sc;
+    __syncthreads();
+    gather<K, COL>(v, sm, l, t);
+    run_stage<K, s>(v, t, tws);
+    __syncthreads();   // every gather of the previous exchange is done
+    scatter<K, s, COL>(v, sm, l, t);
+  });
+  if constexpr (K::S > 1) {
+    __syncthreads();
+    if constexpr (LLF != SLF) {  // switch to the store mapping for the last stage
+      if constexpr (SLF) { l = tid % K::TL; t = tid / K::TL; } else { t = tid % K::TPT; l = tid / K::TPT; }
+    }
+    gather<K, COL>(v, sm, l, t);
+  }
 
   {
     const int line = lt * K::TL + l;
     const bool valid = line < g.nl;
-    if constexpr (TW4) {
-      const unsigned m = (unsigned)line / (unsigned)g.tw_div;
-      const unsigned lomask = (1u << g.tw_lo_bits) - 1u;
-      static_for<0, K::E>([&](auto ec) {
-        constexpr int e = ec;
-        const unsigned x = (unsigned)(t + e * K::TPT) * m;
-        const C w = cmul(__ldg(tw_lo + (x & lomask)), __ldg(tw_hi + (x >> g.tw_lo_bits)));
-        v[e] = cmul(v[e], w);
-      });
-    }
-    if (scale != (T)1) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= scale; });
-    if (g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
-    C* op = out + (long long)b * g.obs + (long long)o * g.oos + (long long)line * g.ols + (long long)t * g.ons;
-    const long long step = (long long)K::TPT * g.ons;
-    if (valid) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; if (g.stream_hint) st_stream(op + e * step, v[e]); else op[e * step] = v[e]; });
+    C* op = out + (long long)b * g.obs + (long long)o * g.oos + (long long)line * g.ols;
+    if constexpr (SLF) op += (long long)t * g.ons; else op += t;
+    const unsigned step_b = (unsigned)((long long)K::TPT * g.ons * (long long)sizeof(C));
+    auto tail = [&](auto cj) {   // last register stage + twiddle + scale + store, cloned on the conjugation
+      constexpr bool CJ = decltype(cj)::value;
+      if constexpr (K::S > 1) run_stage<K, K::S - 1>(v, t, tws);
+      if constexpr (TW4) {
+        const unsigned m = g.tw_from_o ? (unsigned)o : (unsigned)line / (unsigned)g.tw_div;
+        const unsigned lomask = (1u << g.tw_lo_bits) - 1u;
+        auto root = [&](unsigned x) { return cmul(__ldg(tw_lo + (x & lomask)), __ldg(tw_hi + (x >> g.tw_lo_bits))); };
+        constexpr int CH = (K::E < 8) ? K::E : 8;
+        const C stepw = root((unsigned)K::TPT * m);
+        static_for<0, K::E / CH>([&](auto qc) {
+          constexpr int q = qc;
+          C w = root((unsigned)(t + q * CH * K::TPT) * m);
+          static_for<0, CH>([&](auto rc) {
+            constexpr int e = q * CH + rc;
+            v[e] = cmul(v[e], w);
+            if constexpr (rc + 1 < CH) w = cmul(w, stepw);
+          });
+        });
+      }
+      if (scale != (T)1) {
+        const T sy = CJ ? -scale : scale;
+        static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
+      } else if constexpr (CJ) {
+        static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
+      }
+      if (valid) {
+        char* p = reinterpret_cast<char*>(op);
+        static_for<0, K::E>([&](auto ec) {
+          constexpr int e = ec;
+          C* q = SLF ? reinterpret_cast<C*>(p + (unsigned long long)(unsigned)e * step_b) : op + e * K::TPT;
+          if constexpr (HINT & 2) st_stream(q, v[e]); else *q = v[e];
+        });
+      }
+    };
+    if (g.swap_out) tail(std::true_type{}); else tail(std::false_type{});
   }
+}
+
+template <class K, bool LLF, bool SLF, bool TW4>
+__global__ void __launch_bounds__(K::THREADS, K::MINB)
+fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
+                 const cpx_t<typename K::real>* __restrict__ tws, const cpx_t<typename K::real>* __restrict__ tw_lo,
+                 const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale) {
+  using C = cpx_t<typename K::real>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fft_lines_tile<K, LLF, SLF, TW4>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
 }
 
 }  // namespace b200fft

@@ -36,7 +36,7 @@ __global__ void chirp_pack_kernel(const C* __restrict__ in, C* __restrict__ A, c
     if (m < N) {
       const long long line = l0 + l, o = line / I, i = line % I;
       v = in[o * N * I + m * I + i];
-      if (swap_in) v = cswap(v);
+      if (swap_in) v.y = -v.y;
       v = cmul(v, chirp[m]);
     }
     A[l * M + m] = v;
@@ -59,7 +59,7 @@ __global__ void chirp_unpack_kernel(const C* __restrict__ A, C* __restrict__ out
     if (I > 1) { l = idx % nl; k = idx / nl; } else { k = idx % N; l = idx / N; }
     C v = cmul(A[l * M + k], chirp[k]);
     v.x *= scale; v.y *= scale;
-    if (swap_out) v = cswap(v);
+    if (swap_out) v.y = -v.y;
     const long long line = l0 + l, o = line / I, i = line % I;
     out[o * N * I + k * I + i] = v;
   }
@@ -138,7 +138,7 @@ __global__ void mixed_radix_kernel(const MixedParams p, const C* __restrict__ in
     if (line < nlines) {
       const long long o = line / p.I, i = line % p.I;
       v = in[o * p.N * p.I + (long long)n * p.I + i];
-      if (p.swap_in) v = cswap(v);
+      if (p.swap_in) v.y = -v.y;
     }
     buf0[l * N + n] = v;
   }
@@ -182,7 +182,7 @@ __global__ void mixed_radix_kernel(const MixedParams p, const C* __restrict__ in
       const long long o = line / p.I, i = line % p.I;
       C v = src[l * N + n];
       v.x *= scale; v.y *= scale;
-      if (p.swap_out) v = cswap(v);
+      if (p.swap_out) v.y = -v.y;
       out[o * p.N * p.I + (long long)n * p.I + i] = v;
     }
   }
@@ -335,7 +335,7 @@ static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst,
   return cudaGetLastError();
 }
 
-// `inverse` bit 0: swap re/im on load (first pass of an inverse plan); bit 1: swap on store (last pass)
+// `inverse` bit 0: conjugate on load (first pass of an inverse plan); bit 1: conjugate on store (last pass)
 cudaError_t launch_generic(int is_double, const GenericPass& gp, const void* src, void* dst, void* workspace, int inverse,
                            double scale, cudaStream_t stream, long long* nl) {
   if (is_double) return launch_generic_t<double2>(gp, (const double2*)src, (double2*)dst, workspace, inverse, scale, stream, nl);

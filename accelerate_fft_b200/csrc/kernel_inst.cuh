@@ -5,8 +5,9 @@
 
 namespace b200fft {
 
+// everything but the entry point
 template <class K, bool LLF, bool SLF, bool TW4>
-KernelEntry make_entry() {
+KernelEntry describe_cfg() {
   KernelEntry e{};
   e.is_double = sizeof(typename K::real) == 8;
   e.N = K::N; e.E = K::E; e.TL = K::TL; e.threads = K::THREADS;
@@ -17,6 +18,12 @@ KernelEntry make_entry() {
   e.S = K::S;
   for (int i = 0; i < 4; i++) e.rad[i] = K::rad[i];
   e.tw_len = K::TW_LEN;
+  return e;
+}
+
+template <class K, bool LLF, bool SLF, bool TW4>
+KernelEntry make_entry() {
+  KernelEntry e = describe_cfg<K, LLF, SLF, TW4>();
   e.func = reinterpret_cast<const void*>(&fft_lines_kernel<K, LLF, SLF, TW4>);
   return e;
 }

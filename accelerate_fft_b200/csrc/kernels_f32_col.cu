@@ -8,6 +8,7 @@ void register_f32_col(void (*add)(const KernelEntry&)) {
   REG_COL(float, 16, 16, 128, 0, 16);
   REG_COL(float, 32, 8, 32, 0, 8, 4);
   REG_COL(float, 64, 8, 16, 0, 8, 8);
+  REG_COL(float, 64, 16, 32, 0, 16, 4);               // v1: 32 lines (256 B runs), 16 KB tiles
   REG_COL(float, 128, 16, 16, 0, 16, 8);
   REG_COL(float, 256, 16, 16, 0, 16, 16);
   REG_COL(float, 512, 32, 16, 0, 32, 16);             // v0: 256 thr x 128 regs, one exchange

@@ -20,6 +20,7 @@
 #include "generic.h"
 #include "registry.h"
 #include "fft_kernel.cuh"
+#include "fused_kernel.cuh"
 
 namespace b200fft {
 
@@ -37,6 +38,11 @@ static void add_entry(const KernelEntry& e_) {
     if (o.is_double == e.is_double && o.N == e.N && o.flavor == e.flavor && o.tw4 == e.tw4) e.variant++;
   reg().push_back(e);
 }
+static std::vector<FusedEntry>& freg() {
+  static std::vector<FusedEntry> r;
+  return r;
+}
+static void add_fused(const FusedEntry& e) { freg().push_back(e); }
 static std::once_flag g_reg_once;
 static void ensure_registry() {
   std::call_once(g_reg_once, [] {
@@ -47,6 +53,7 @@ static void ensure_registry() {
     register_f64_large(add_entry);
     register_f64_col(add_entry);
     register_ring(add_entry);
+    register_fused(add_fused);
   });
 }
 
@@ -76,6 +83,19 @@ const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int pr
     if (e.variant == want) return &e;
   }
   return first;
+}
+const FusedEntry* find_fused(int is_double, int NA, int flavA, int twA, int NB, int flavB) {
+  ensure_registry();
+  // Opt-in (B200FFT_FUSED=1).  Measured on B200 (profiles/r01_fused_l2_staging.txt): the L2 staging works -- ncu
+  // shows exactly one HBM read + one HBM write of the array for both phases together -- but the c64 phases are
+  // instruction-issue bound (~55 issued instructions per point and phase, 70 % issue utilisation), not HBM
+  // bound, so removing the HBM round trip does not make them faster yet: cfg3 600 us fused vs 549 us unfused.
+  const char* on = getenv("B200FFT_FUSED");
+  if (!(on && atoi(on))) return nullptr;
+  for (const auto& e : freg())
+    if (e.a.is_double == is_double && e.a.N == NA && e.a.flavor == flavA && e.a.tw4 == twA && e.b.N == NB && e.b.flavor == flavB && e.b.tw4 == 0)
+      return &e;
+  return nullptr;
 }
 int list_kernels(const KernelEntry** out, int max) {
   ensure_registry();
@@ -120,7 +140,7 @@ static cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3 };
+enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3, PK_FUSED2 = 4 };
 
 struct Pass {
   int kind = PK_LINES;
@@ -135,6 +155,12 @@ struct Pass {
   void* tw_lo = nullptr;           // device: four-step twiddle tables
   void* tw_hi = nullptr;
   long long ntiles = 0;
+  const FusedEntry* fz = nullptr;  // PK_FUSED2
+  FusedParams fp{};
+  void* twsB = nullptr;            // PK_FUSED2: stage twiddles of phase B (tws = phase A)
+  bool mid_in_dst = false;         // PK_FUSED2: phase A writes into dst (in place there) instead of scratch slots
+  int fused_grid = 0;              // PK_FUSED2: persistent CTAs
+  bool first_swap_a = true;
   std::string desc;
 };
 
@@ -153,6 +179,7 @@ struct b200fft_plan_s {
   std::vector<void*> dev_allocs;
   size_t scratch_bytes = 0;   // main scratch (same size as the array) if any pass uses BUF_SCRATCH
   size_t extra_bytes = 0;     // bluestein workspace
+  size_t band_bytes = 0;      // fused passes: two L2-resident band slots + the ticket / progress counters
 };
 
 namespace b200fft {
@@ -244,7 +271,10 @@ struct Builder {
     ps.kind = PK_LINES;
     ps.k = k;
     g.ntl = (g.nl + k->TL - 1) / k->TL;
-    { const char* sh = getenv("B200FFT_STREAM_HINT"); g.stream_hint = sh ? atoi(sh) : 0; }
+    {  // the kernels address a thread's points with 32-bit byte strides
+      const long long tpt = k->N / k->E, esz = p->is_double ? 16 : 8;
+      if (tpt * g.ins * esz >= (1LL << 32) || tpt * g.ons * esz >= (1LL << 32)) { err = B200FFT_INVALID_SIZE; return false; }
+    }
     ps.g = g;
     ps.inplace_ok = inplace_ok;
     ps.tws = make_stage_twiddles(p, k);
@@ -269,6 +299,182 @@ struct Builder {
     }
     push(ps);
     return true;
+  }
+
+
+  // ---- two phases in one launch with an L2-resident intermediate (fused_kernel.cuh) -----------
+  static size_t counters_bytes(int nbands) { return (((size_t)(1 + 2 * nbands) * 4) + 255) / 256 * 256; }
+  static long long band_target_bytes() {
+    const char* e = getenv("B200FFT_BAND_MB");
+    return (long long)(e && atoi(e) > 0 ? atoi(e) : 2) << 20;
+  }
+  static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; }
+
+  bool fused_pass(const FusedEntry* fz, Geom ga, Geom gb, FusedParams fp, long long twL, bool mid_in_dst, bool inplace_ok, const char* what) {
+    Pass ps;
+    ps.kind = PK_FUSED2;
+    ps.fz = fz;
+    ga.ntl = (ga.nl + fz->a.TL - 1) / fz->a.TL;
+    gb.ntl = (gb.nl + fz->b.TL - 1) / fz->b.TL;
+    {
+      const long long esz = p->is_double ? 16 : 8, ta = fz->a.N / fz->a.E, tb = fz->b.N / fz->b.E;
+      if (ta * ga.ins * esz >= (1LL << 32) || ta * ga.ons * esz >= (1LL << 32) || tb * gb.ins * esz >= (1LL << 32) ||
+          tb * gb.ons * esz >= (1LL << 32))
+        return false;
+    }
+    // (phase A streams its input from HBM with evict-first loads and leaves its output in L2; phase B reads L2
+    //  with ld.global.cg and streams its output to HBM with evict-first stores: compile-time in fused_kernel.cuh)
+    fp.la = env_int("B200FFT_FUSED_LA", 8);
+    if (fp.la > fp.nbands) fp.la = fp.nbands;
+    fp.nslots = env_int("B200FFT_FUSED_SLOTS", fp.la + 6);
+    if (fp.nslots < fp.la + 1) fp.nslots = fp.la + 1;
+    const long long nA = (long long)ga.nb * ga.no * ga.ntl, nB = (long long)gb.nb * gb.no * gb.ntl;
+    // tickets cover ~64 KB of tiles
+    auto per_ticket = [&](const KernelEntry& k, const char* env) {
+      const long long tile_bytes = (long long)k.N * k.TL * (long long)esize(p);
+      (void)tile_bytes;   // measured: grouping tiles under one ticket only shrinks the pool of runnable tickets
+      long long kk = env_int(env, 1);
+      return (int)(kk < 1 ? 1 : (kk > 16 ? 16 : kk));
+    };
+    fp.ka = per_ticket(fz->a, "B200FFT_FUSED_KA");
+    fp.kb = per_ticket(fz->b, "B200FFT_FUSED_KB");
+    const long long total = (long long)fp.nbands * ((nA + fp.ka - 1) / fp.ka + (nB + fp.kb - 1) / fp.kb);
+    if (nA >= (1LL << 30) || nB >= (1LL << 30) || total >= (1LL << 31)) return false;
+    ps.tws = make_stage_twiddles(p, &fz->a);
+    ps.twsB = make_stage_twiddles(p, &fz->b);
+    if (fz->a.tw4) make_fourstep_tables(p, twL, &ga.tw_lo_bits, &ps.tw_lo, &ps.tw_hi);
+    fp.a = ga; fp.b = gb;
+    fp.nA = (int)nA; fp.nB = (int)nB;
+    ps.fp = fp;
+    ps.ntiles = total;
+    ps.mid_in_dst = mid_in_dst;
+    ps.inplace_ok = inplace_ok;
+    const size_t need = counters_bytes(fp.nbands) + (mid_in_dst ? 0 : (size_t)fp.nslots * fp.slot_elems * esize(p));
+    if (need > p->band_bytes) p->band_bytes = need;
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "%s: fused A[N=%d %s%s E=%d TL=%d] -> %s -> B[N=%d %s E=%d TL=%d] threads=%d smem=%zu bands=%d tiles/band=%lld+%lld",
+             what, fz->a.N, fz->a.flavor == FL_ROW ? "row" : "col", fz->a.tw4 ? "+tw" : "", fz->a.E, fz->a.TL,
+             mid_in_dst ? "L2 (in place in dst)" : "L2 band slots", fz->b.N, fz->b.flavor == FL_COL ? "col" : "trans", fz->b.E, fz->b.TL,
+             fz->threads, fz->smem, fp.nbands, nA, nB);
+    snprintf(buf + strlen(buf), sizeof buf - strlen(buf), " tiles/ticket=%d+%d", fp.ka, fp.kb);
+    ps.desc = buf;
+    if (!mid_in_dst) {
+      snprintf(buf, sizeof buf, " slot=%.1f MiB x%d lookahead=%d", (double)fp.slot_elems * esize(p) / 1048576.0, fp.nslots, fp.la);
+      ps.desc += buf;
+    }
+    push(ps);
+    return true;
+  }
+
+  // strided axis [O][N][I], N = N1*N2: phase A = FFT over n1 (+ twiddle w_N^(k1 n2)) for a band of Wb columns,
+  // phase B = FFT over n2 with the index-reversed store.  In place at band granularity.
+  bool try_fused_strided(long long O, long long N, long long I) {
+    long long N1, N2;
+    if (!split2(N, 1024, &N1, &N2)) return false;
+    const FusedEntry* fz = find_fused(p->is_double, (int)N1, FL_COL, 1, (int)N2, FL_COL);
+    if (!fz) return false;
+    long long Wb = band_target_bytes() / (N * (long long)esize(p));
+    while (Wb & (Wb - 1)) Wb &= Wb - 1;          // floor to a power of two
+    const long long tl = fz->a.TL > fz->b.TL ? fz->a.TL : fz->b.TL;
+    if (Wb < tl) Wb = tl;
+    while (Wb > tl && I % Wb) Wb >>= 1;
+    if (I % Wb || Wb % fz->a.TL || Wb % fz->b.TL) return false;
+    if (N2 * I >= (1LL << 40)) return false;
+    Geom ga{}, gb{};
+    ga.nb = 1; ga.no = (int)N2; ga.nl = (int)Wb;
+    ga.ios = I; ga.ils = 1; ga.ins = N2 * I;
+    ga.oos = Wb; ga.ols = 1; ga.ons = N2 * Wb;
+    ga.tw_div = 1; ga.tw_from_o = 1;
+    gb.nb = 1; gb.no = (int)N1; gb.nl = (int)Wb;
+    gb.ios = N2 * Wb; gb.ils = 1; gb.ins = Wb;
+    gb.oos = I; gb.ols = 1; gb.ons = N1 * I;
+    gb.tw_div = 1;
+    FusedParams fp{};
+    fp.nbi = (int)(I / Wb);
+    if (O * fp.nbi >= (1LL << 24)) return false;
+    fp.nbands = (int)(O * fp.nbi);
+    fp.a_in_bo = N * I; fp.a_in_bi = Wb;
+    fp.b_out_bo = N * I; fp.b_out_bi = Wb;
+    fp.slot_elems = N * Wb;
+    return fused_pass(fz, ga, gb, fp, N, false, true, "4step-strided");
+  }
+
+  // contiguous lines [O][N], N = N1*N2 <= 2^20: a band is a group of whole transforms (<= ~8 MiB)
+  bool try_fused_contig2(long long O, long long N) {
+    const int lg = ilog2(N);
+    const long long N1 = 1LL << (lg / 2), N2 = N / N1;
+    const FusedEntry* fz = find_fused(p->is_double, (int)N1, FL_COL, 1, (int)N2, FL_TRANS);
+    if (!fz) return false;
+    long long nbat = band_target_bytes() / (N * (long long)esize(p));
+    if (nbat < 1) nbat = 1;
+    if (nbat > O) nbat = O;
+    while (O % nbat) nbat--;
+    if (O / nbat >= (1LL << 24)) return false;
+    Geom ga{}, gb{};
+    ga.nb = (int)nbat; ga.no = 1; ga.nl = (int)N2;
+    ga.ibs = N; ga.ils = 1; ga.ins = N2;
+    ga.obs = N; ga.ols = 1; ga.ons = N2;
+    ga.tw_div = 1;
+    gb.nb = (int)nbat; gb.no = 1; gb.nl = (int)N1;
+    gb.ibs = N; gb.ils = N2; gb.ins = 1;
+    gb.obs = N; gb.ols = 1; gb.ons = N1;
+    gb.tw_div = 1;
+    FusedParams fp{};
+    fp.nbi = 1;
+    fp.nbands = (int)(O / nbat);
+    fp.a_in_bo = nbat * N; fp.b_out_bo = nbat * N;
+    fp.slot_elems = nbat * N;
+    return fused_pass(fz, ga, gb, fp, N, false, true, "4step");
+  }
+
+  // second and third factor of a three-factor contiguous transform [O][N1][M], M = N2*N3, fused over bands of
+  // Rb rows k1: phase A = FFT over n2 (+ twiddle w_M^(k2 n3)), phase B = rows n3 with the transposed store
+  // X[k1 + N1 k2 + N1 N2 k3] whose contiguous runs are the band's Rb values of k1.
+  bool try_fused_contig3_tail(long long O, long long N, long long N1, long long N2, long long N3) {
+    const FusedEntry* fz = find_fused(p->is_double, (int)N2, FL_COL, 1, (int)N3, FL_TRANS);
+    if (!fz) return false;
+    const long long M = N2 * N3;
+    long long Rb = fz->b.TL;
+    { const char* e = getenv("B200FFT_ROWS_PER_BAND"); if (e && atoi(e) > 0) Rb = atoi(e); }
+    if (N1 % Rb) return false;
+    Geom ga{}, gb{};
+    ga.nb = 1; ga.no = (int)Rb; ga.nl = (int)N3;
+    ga.ios = M; ga.ils = 1; ga.ins = N3;
+    ga.oos = M; ga.ols = 1; ga.ons = N3;
+    ga.tw_div = 1;
+    gb.nb = 1; gb.no = (int)N2; gb.nl = (int)Rb;
+    gb.ios = N3; gb.ils = M; gb.ins = 1;
+    gb.oos = N1; gb.ols = 1; gb.ons = N1 * N2;
+    gb.tw_div = 1;
+    FusedParams fp{};
+    fp.nbi = (int)(N1 / Rb);
+    if (O * fp.nbi >= (1LL << 24)) return false;
+    fp.nbands = (int)(O * fp.nbi);
+    fp.a_in_bo = N; fp.a_in_bi = Rb * M;
+    fp.b_out_bo = N; fp.b_out_bi = Rb;
+    fp.slot_elems = Rb * M;
+    return fused_pass(fz, ga, gb, fp, M, false, false, "6step-BC");
+  }
+
+  // x rows + y columns of each z-plane of a [D][H][W] array, the plane staying in L2 between the two
+  bool try_fused_plane(long long D, long long H, long long W) {
+    if (!is_pow2(H) || !is_pow2(W) || D >= (1LL << 24)) return false;
+    const FusedEntry* fz = find_fused(p->is_double, (int)W, FL_ROW, 0, (int)H, FL_COL);
+    if (!fz) return false;
+    Geom ga{}, gb{};
+    ga.nb = 1; ga.no = 1; ga.nl = (int)H;
+    ga.ils = W; ga.ins = 1; ga.ols = W; ga.ons = 1;
+    ga.tw_div = 1;
+    gb.nb = 1; gb.no = 1; gb.nl = (int)W;
+    gb.ils = 1; gb.ins = W; gb.ols = 1; gb.ons = W;
+    gb.tw_div = 1;
+    FusedParams fp{};
+    fp.nbi = 1;
+    fp.nbands = (int)D;
+    fp.a_in_bo = H * W; fp.mid_bo = H * W; fp.b_out_bo = H * W;
+    fp.slot_elems = 0;
+    return fused_pass(fz, ga, gb, fp, 0, true, true, "plane-xy");
   }
 
   int max_col_n() const { return 2048; }   // longest strided axis done in one pass (>= 64 B runs)
@@ -315,6 +521,7 @@ struct Builder {
 
   // four-step along a strided axis: [O][N][I], N = N1*N2, n = n1*N2 + n2, k = k1 + N1*k2
   void fourstep_strided(long long O, long long N, long long I) {
+    if (try_fused_strided(O, N, I)) return;
     long long N1, N2;
     // small sub-lengths keep the [N][TL] tiles small; cap at 1024 so TL stays >= 8
     if (!split2(N, 1024, &N1, &N2)) { err = B200FFT_NOT_SUPPORTED; return; }
@@ -342,6 +549,7 @@ struct Builder {
     const long long lim = 1024;  // column / transposing tiles of <= 1024 points keep >= 64 B contiguous runs
     int lg = ilog2(N);
     if (N <= lim * lim) {
+      if (try_fused_contig2(O, N)) return;
       long long N1 = 1LL << (lg / 2), N2 = N / N1;
       {  // A: FFT over n1 (stride N2), lines n2, twiddle w_N^(k1*n2)
         Geom g{};
@@ -365,6 +573,13 @@ struct Builder {
     // three factors: n = n1*M + n2*N3 + n3 (M = N2*N3), k = k1 + N1*k2 + N1*N2*k3
     int a = lg / 3, b = (lg - a) / 2, c = lg - a - b;
     long long N1 = 1LL << c, N2 = 1LL << b, N3 = 1LL << a;  // largest first: column tiles are cheapest to keep big
+    bool fuse_tail = false;
+    for (int lm = 18; lm >= 16 && !fuse_tail; lm--) {      // prefer a tail that has a fused (L2-staged) kernel pair
+      const long long n2 = 1LL << (lm / 2), n3 = 1LL << (lm - lm / 2), n1 = N >> lm;
+      if (n1 >= 16 && n1 <= max_col_n() && find_fused(p->is_double, (int)n2, FL_COL, 1, (int)n3, FL_TRANS)) {
+        N1 = n1; N2 = n2; N3 = n3; fuse_tail = true;
+      }
+    }
     long long M = N2 * N3;
     if (O * N1 >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
     {  // A: FFT over n1 (stride M), lines m < M, twiddle w_N^(k1*m)
@@ -375,6 +590,7 @@ struct Builder {
       g.tw_div = 1;
       if (!lines_pass((int)N1, FL_COL, true, g, N, true, 0, "6step-A")) { err = B200FFT_INTERNAL_ERROR; return; }
     }
+    if (fuse_tail && try_fused_contig3_tail(O, N, N1, N2, N3)) return;
     {  // B: for each (o,k1): FFT over n2 (stride N3), lines n3, twiddle w_M^(k2*n3)
       Geom g{};
       g.nb = 1; g.no = (int)(O * N1); g.nl = (int)N3;
@@ -440,6 +656,17 @@ static int set_func_attrs(b200fft_plan_s* p) {
     if (ps.kind == PK_LINES && ps.k->smem > 48 * 1024) {
       if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess)
         return B200FFT_INTERNAL_ERROR;
+    }
+    if (ps.kind == PK_FUSED2) {
+      if (ps.fz->smem > 48 * 1024 &&
+          cudaFuncSetAttribute(ps.fz->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.fz->smem) != cudaSuccess)
+        return B200FFT_INTERNAL_ERROR;
+      int dev = 0, nsm = 0, occ = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.fz->func, ps.fz->threads, ps.fz->smem) != cudaSuccess || occ < 1)
+        return B200FFT_INTERNAL_ERROR;
+      long long grid = (long long)nsm * occ;
+      ps.fused_grid = (int)(grid < ps.ntiles ? grid : ps.ntiles);
     }
     if (ps.kind == PK_LINES && ps.ring) {
       int dev = 0, nsm = 0, occ = 0;
@@ -539,8 +766,10 @@ int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type
   auto* p = new b200fft_plan_s;
   p->is_double = dbl; p->rank = 3; p->dims[0] = d; p->dims[1] = h; p->dims[2] = w; p->total = d * h * w;
   Builder b{p};
-  b.axis(d * h, w, 1);   // x
-  b.axis(d, h, w);       // y
+  if (!b.try_fused_plane(d, h, w)) {
+    b.axis(d * h, w, 1);   // x
+    b.axis(d, h, w);       // y
+  }
   b.axis(1, d, h * w);   // z
   return finish_plan(p, b, plan);
 }
@@ -556,6 +785,13 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
   if (p->extra_bytes && scratch_alloc(&extra, p->extra_bytes, stream) != cudaSuccess) {
     cudaGetLastError();
     if (scratch) cudaFreeAsync(scratch, stream);
+    return B200FFT_ALLOC_FAILED;
+  }
+  void* band = nullptr;
+  if (p->band_bytes && scratch_alloc(&band, p->band_bytes, stream) != cudaSuccess) {
+    cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, stream);
+    if (extra) cudaFreeAsync(extra, stream);
     return B200FFT_ALLOC_FAILED;
   }
   const int inverse = direction == B200FFT_INVERSE;
@@ -583,6 +819,21 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
         ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
       }
       g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (ps.kind == PK_FUSED2) {
+      FusedParams fp = ps.fp;
+      fp.a.swap_in = inverse && first;
+      fp.b.swap_out = inverse && last;
+      const size_t cb = Builder::counters_bytes(fp.nbands);
+      unsigned* counters = (unsigned*)band;
+      void* mid = ps.mid_in_dst ? dst : (void*)((char*)band + cb);
+      ce = cudaMemsetAsync(counters, 0, cb, stream);
+      float scf = (float)sc;
+      double scd = sc;
+      void* args[] = {&fp, (void*)&src, (void*)&dst, (void*)&mid, (void*)&ps.tws, (void*)&ps.twsB, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                      p->is_double ? (void*)&scd : (void*)&scf, (void*)&counters};
+      if (ce == cudaSuccess)
+        ce = cudaLaunchCooperativeKernel(ps.fz->func, dim3((unsigned)ps.fused_grid), dim3(ps.fz->threads), args, ps.fz->smem, stream);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (ps.kind == PK_COPY) {
       long long nl = 0;
       ce = launch_copy_scale(p->is_double, src, dst, p->total, sc, stream, &nl);
@@ -596,6 +847,7 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
   }
   if (scratch) cudaFreeAsync(scratch, stream);
   if (extra) cudaFreeAsync(extra, stream);
+  if (band) cudaFreeAsync(band, stream);
   if (status != B200FFT_SUCCESS) cudaGetLastError();
   return status;
 }
@@ -655,7 +907,7 @@ int b200fftTrimScratch(void) {
   return B200FFT_SUCCESS;
 }
 
-size_t b200fftScratchBytes(b200fftHandle p) { return p ? p->scratch_bytes + p->extra_bytes : 0; }
+size_t b200fftScratchBytes(b200fftHandle p) { return p ? p->scratch_bytes + p->extra_bytes + p->band_bytes : 0; }
 int b200fftNumPasses(b200fftHandle p) { return p ? (int)p->passes.size() : 0; }
 int64_t b200fftKernelLaunches(void) { return g_launches.load(); }
 

@@ -23,6 +23,16 @@ struct KernelEntry {
 
 template <class K, bool LLF, bool SLF, bool TW4> KernelEntry make_entry();
 
+// two line-kernel phases fused into one launch (fused_kernel.cuh)
+struct FusedEntry {
+  KernelEntry a, b;   // func unused; flavor / tw4 / N identify the phases
+  const void* func;
+  int threads;
+  size_t smem;
+};
+const FusedEntry* find_fused(int is_double, int NA, int flavA, int twA, int NB, int flavB);
+void register_fused(void (*add)(const FusedEntry&));
+
 const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int prefer_tl);
 int list_kernels(const KernelEntry** out, int max);
 

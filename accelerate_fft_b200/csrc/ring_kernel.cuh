@@ -117,7 +117,7 @@ fft_ring_rows_kernel(const Geom g, const cpx_t<typename R::Base::real>* __restri
     mbar_wait(&full[s], (uint32_t)((k / R::NS) & 1));
     C v[K::E];
     static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = sm[l * K::N + t + e * K::TPT]; });
-    if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
+    if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
     group_bar(bar_id, K::THREADS);  // the linear tile is consumed; the buffer becomes the exchange space
 
     // all stages but the last, exchanging through the stage buffer
@@ -146,7 +146,7 @@ fft_ring_rows_kernel(const Geom g, const cpx_t<typename R::Base::real>* __restri
 
     run_stage<K, K::S - 1>(v, t, tws);
     if (scale != (T)1) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= scale; });
-    if (g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cswap(v[e]); });
+    if (g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
     if (valid) {
       C* op = out + line * K::N + t;
       static_for<0, K::E>([&](auto ec) { constexpr int e = ec; st_stream(op + e * K::TPT, v[e]); });
