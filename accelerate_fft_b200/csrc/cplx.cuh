@@ -32,6 +32,62 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
 template <typename C> __device__ __forceinline__ C mul_mi(C a) { return C{a.y, -a.x}; }  // a * (-i)
 template <typename C> __device__ __forceinline__ C cswap(C a) { return C{a.y, a.x}; }
 
+// Blackwell packed FP32: add/sub/mul/fma.f32x2 work on a (lo, hi) register pair -- one issue slot for both halves
+// of a complex number -- and ptxas folds half swaps and per-half negations into the operand modifiers
+// (FADD2 / FFMA2 Ra.F32x2.LO_HI.NP ...), so -i*a and conj cost nothing.  The c64 kernels are bound by
+// instruction issue, not by the FP32 pipe (profiles/r01_sass_mix_*.txt), hence every complex add and twiddle
+// multiply below goes through these; c128 keeps the scalar DADD/DFMA forms.
+#ifndef B200FFT_NO_F32X2
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return upk2(sub2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+// (a.x w.x - a.y w.y, a.x w.y + a.y w.x) = a * (w.x, w.x) + (a.y, a.x) * (-w.y, w.y)
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return upk2(fma2(pk2(a.x, a.y), pk2(w.x, w.x), mul2(pk2(a.y, a.x), pk2(-w.y, w.y))));
+}
+// a + (-i) b and a - (-i) b: the two odd outputs of a radix-4 butterfly, one FFMA2 each
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return upk2(fma2(pk2(b.y, b.x), pk2(1.f, -1.f), pk2(a.x, a.y))); }
+__device__ __forceinline__ float2 csub_mi(float2 a, float2 b) { return upk2(fma2(pk2(b.y, b.x), pk2(-1.f, 1.f), pk2(a.x, a.y))); }
+// a * h, or (-i a) * h when rot
+__device__ __forceinline__ float2 cscale(float2 a, float h, bool rot = false) {
+  return rot ? upk2(mul2(pk2(a.y, a.x), pk2(h, -h))) : upk2(mul2(pk2(a.x, a.y), pk2(h, h)));
+}
+#endif
+template <typename C> __device__ __forceinline__ C cadd_mi(C a, C b) { return C{a.x + b.y, a.y - b.x}; }
+template <typename C> __device__ __forceinline__ C csub_mi(C a, C b) { return C{a.x - b.y, a.y + b.x}; }
+template <typename C, typename T> __device__ __forceinline__ C cscale(C a, T h, bool rot = false) {
+  return rot ? C{a.y * h, -a.x * h} : C{a.x * h, a.y * h};
+}
+
 // bulk data is touched once per launch: evict-first loads / stores keep the reused twiddle tables cached
 __device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
 __device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
@@ -72,13 +128,13 @@ __device__ __forceinline__ C mul_w32(C a) {
   else if constexpr (m == 8) return C{a.y, -a.x};
   else if constexpr (m == 16) return C{-a.x, -a.y};
   else if constexpr (m == 24) return C{-a.y, a.x};
-  else if constexpr (m == 4) { constexpr T h = (T)0.70710678118654752440084436210485; return C{(a.x + a.y) * h, (a.y - a.x) * h}; }
-  else if constexpr (m == 12) { constexpr T h = (T)0.70710678118654752440084436210485; return C{(a.y - a.x) * h, -(a.x + a.y) * h}; }
-  else if constexpr (m == 20) { constexpr T h = (T)0.70710678118654752440084436210485; return C{-(a.x + a.y) * h, (a.x - a.y) * h}; }
-  else if constexpr (m == 28) { constexpr T h = (T)0.70710678118654752440084436210485; return C{(a.x - a.y) * h, (a.x + a.y) * h}; }
+  else if constexpr (m == 4) { constexpr T h = (T)0.70710678118654752440084436210485; return cscale(cadd_mi(a, a), h); }     // (x+y, y-x) h
+  else if constexpr (m == 12) { constexpr T h = (T)0.70710678118654752440084436210485; return cscale(cadd_mi(a, a), h, true); }
+  else if constexpr (m == 20) { constexpr T h = (T)0.70710678118654752440084436210485; return cscale(cadd_mi(a, a), -h); }
+  else if constexpr (m == 28) { constexpr T h = (T)0.70710678118654752440084436210485; return cscale(cadd_mi(a, a), -h, true); }
   else {
     constexpr T wr = (T)w32_re(m), wi = (T)w32_im(m);
-    return C{a.x * wr - a.y * wi, a.x * wi + a.y * wr};
+    return cmul(a, C{wr, wi});
   }
 }
 
@@ -91,8 +147,8 @@ __device__ __forceinline__ void dft(C (&x)[R]) {
     x[0] = cadd(a, b); x[1] = csub(a, b);
   } else if constexpr (R == 4) {
     C t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
-    C t2 = cadd(x[1], x[3]), t3 = mul_mi(csub(x[1], x[3]));
-    x[0] = cadd(t0, t2); x[1] = cadd(t1, t3); x[2] = csub(t0, t2); x[3] = csub(t1, t3);
+    C t2 = cadd(x[1], x[3]), t3 = csub(x[1], x[3]);
+    x[0] = cadd(t0, t2); x[1] = cadd_mi(t1, t3); x[2] = csub(t0, t2); x[3] = csub_mi(t1, t3);
   } else if constexpr (R == 8) {
     C e[4] = {x[0], x[2], x[4], x[6]};
     C o[4] = {x[1], x[3], x[5], x[7]};
@@ -118,8 +174,8 @@ __device__ __forceinline__ void dft(C (&x)[R]) {
       C a2 = mul_w32<2 * u * k>(s2[k]);
       C a3 = mul_w32<3 * u * k>(s3[k]);
       C t0 = cadd(a0, a2), t1 = csub(a0, a2);
-      C t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
-      x[k] = cadd(t0, t2); x[k + M] = cadd(t1, t3); x[k + 2 * M] = csub(t0, t2); x[k + 3 * M] = csub(t1, t3);
+      C t2 = cadd(a1, a3), t3 = csub(a1, a3);
+      x[k] = cadd(t0, t2); x[k + M] = cadd_mi(t1, t3); x[k + 2 * M] = csub(t0, t2); x[k + 3 * M] = csub_mi(t1, t3);
     });
   }
 }

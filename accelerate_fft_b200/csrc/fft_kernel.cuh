@@ -22,6 +22,9 @@ struct Geom {
   int tw_from_o;                 // four-step multiplier is the outer index o instead of line / tw_div
   int tw_lo_bits;
   int swap_in, swap_out;         // conjugate on load / on store: inverse = conj(fwd(conj(x)))
+  // PRE2 ("row pair") kernels only: the tile's input is x[n] + (-1)^line * x[n + pre2_off] -- the radix-2 first
+  // stage of a strided axis of length 2*M folded into the row pass; the result is multiplied by w_{2M}^(line*o)
+  long long pre2_off;
 };
 
 template <typename T_, int N_, int E_, int TL_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
@@ -134,6 +137,8 @@ __device__ __forceinline__ void gather(C (&v)[K::E], const C* sm, int l, int t) 
 //      points of a line are contiguous (ins == 1, compile-time offsets).
 // SLF: same for the store side (ols == 1, otherwise ons == 1).
 // TW4: multiply the result by the four-step twiddle.
+// PRE2: row kernels with TL == 1 only -- see Geom::pre2_off.  Two consecutive tiles (line = 0, 1) read the same
+//      two rows (the second reader hits L2) and produce the two outputs of the radix-2 butterfly between them.
 // CG:  read the input with ld.global.cg (L2 only) -- for tiles another CTA of the SAME launch produced.
 // HINT: bit 0 evict-first loads (ld.global.cs), bit 1 evict-first stores (compile-time: no dead twins).
 //
@@ -142,7 +147,7 @@ __device__ __forceinline__ void gather(C (&v)[K::E], const C* sm, int l, int t) 
 // table reads per point (measured: the +tw passes of cfg4 ran at 2.8-4.7 TB/s against 5.5 without);
 // instead one anchor per 8 points comes from the two-level table and the 7 in between from a running
 // product with the step w_L^(TPT*m): 2 + E/4 table reads per thread instead of 2E, error <= 8 ulp.
-template <class K, bool LLF, bool SLF, bool TW4, bool CG = false, int HINT = 0>
+template <class K, bool LLF, bool SLF, bool TW4, bool CG = false, int HINT = 0, bool PRE2 = false>
 __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, const cpx_t<typename K::real>* __restrict__ in,
                                                cpx_t<typename K::real>* __restrict__ out, const cpx_t<typename K::real>* __restrict__ tws,
                                                const cpx_t<typename K::real>* __restrict__ tw_lo,
@@ -151,6 +156,7 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
   using T = typename K::real;
   using C = cpx_t<T>;
   static_assert(LLF == SLF || K::S >= 2, "the transposing variant needs an exchange to re-map threads");
+  static_assert(!PRE2 || (!LLF && !SLF && !TW4 && K::TL == 1), "PRE2 is a row-kernel option");
   constexpr bool COL = LLF && SLF;   // the shared-memory layout is columnar only when both ends are line-fastest
   const int tid = threadIdx.x;
   int lt, o, b;
@@ -185,6 +191,12 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
         if constexpr (CG) x = __ldcg(q);
         else if constexpr (HINT & 1) x = ld_stream(q);
         else x = *q;
+        if constexpr (PRE2) {
+          const C y = (ip + g.pre2_off)[e * K::TPT];
+          const T sg = (lt & 1) ? (T)-1 : (T)1;
+          x.x = fma(sg, y.x, x.x);
+          x.y = fma(sg, y.y, x.y);
+        }
         if constexpr (CJ) x.y = -x.y;
         v[e] = x;
       });
@@ -236,6 +248,13 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
           });
         });
       }
+      if constexpr (PRE2) {
+        if (lt & 1) {   // CTA-uniform: the odd output of the pair carries the twiddle w_{2M}^o
+          const unsigned lomask = (1u << g.tw_lo_bits) - 1u;
+          const C w = cmul(__ldg(tw_lo + ((unsigned)o & lomask)), __ldg(tw_hi + ((unsigned)o >> g.tw_lo_bits)));
+          static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = cmul(v[e], w); });
+        }
+      }
       if (scale != (T)1) {
         const T sy = CJ ? -scale : scale;
         static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
@@ -255,14 +274,14 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
   }
 }
 
-template <class K, bool LLF, bool SLF, bool TW4>
+template <class K, bool LLF, bool SLF, bool TW4, bool PRE2 = false>
 __global__ void __launch_bounds__(K::THREADS, K::MINB)
 fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
                  const cpx_t<typename K::real>* __restrict__ tws, const cpx_t<typename K::real>* __restrict__ tw_lo,
                  const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale) {
   using C = cpx_t<typename K::real>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  fft_lines_tile<K, LLF, SLF, TW4>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
+  fft_lines_tile<K, LLF, SLF, TW4, false, 0, PRE2>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
 }
 
 }  // namespace b200fft

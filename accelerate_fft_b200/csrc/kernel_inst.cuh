@@ -6,12 +6,12 @@
 namespace b200fft {
 
 // everything but the entry point
-template <class K, bool LLF, bool SLF, bool TW4>
+template <class K, bool LLF, bool SLF, bool TW4, bool PRE2 = false>
 KernelEntry describe_cfg() {
   KernelEntry e{};
   e.is_double = sizeof(typename K::real) == 8;
   e.N = K::N; e.E = K::E; e.TL = K::TL; e.threads = K::THREADS;
-  e.flavor = (LLF && SLF) ? FL_COL : (!LLF && SLF) ? FL_TRANS : FL_ROW;
+  e.flavor = PRE2 ? FL_ROWPAIR : (LLF && SLF) ? FL_COL : (!LLF && SLF) ? FL_TRANS : FL_ROW;
   e.tw4 = TW4;
   e.minb = K::MINB;
   e.smem = K::template smem_bytes<(LLF && SLF)>();
@@ -21,10 +21,10 @@ KernelEntry describe_cfg() {
   return e;
 }
 
-template <class K, bool LLF, bool SLF, bool TW4>
+template <class K, bool LLF, bool SLF, bool TW4, bool PRE2 = false>
 KernelEntry make_entry() {
-  KernelEntry e = describe_cfg<K, LLF, SLF, TW4>();
-  e.func = reinterpret_cast<const void*>(&fft_lines_kernel<K, LLF, SLF, TW4>);
+  KernelEntry e = describe_cfg<K, LLF, SLF, TW4, PRE2>();
+  e.func = reinterpret_cast<const void*>(&fft_lines_kernel<K, LLF, SLF, TW4, PRE2>);
   return e;
 }
 
@@ -33,6 +33,7 @@ KernelEntry make_ring_entry();
 
 #define REG_ROW(...)   add(make_entry<Cfg<__VA_ARGS__>, false, false, false>())
 #define REG_COL(...)   add(make_entry<Cfg<__VA_ARGS__>, true, true, false>()); add(make_entry<Cfg<__VA_ARGS__>, true, true, true>())
+#define REG_PAIR(...)  add(make_entry<Cfg<__VA_ARGS__>, false, false, false, true>())
 #define REG_TRANS(...) add(make_entry<Cfg<__VA_ARGS__>, false, true, false>())
 
 }  // namespace b200fft

@@ -18,7 +18,10 @@ void register_f32_col(void (*add)(const KernelEntry&)) {
   REG_COL(float, 1024, 16, 16, 0, 16, 16, 4);         // v2: 1024 thr, 128 B runs
   REG_COL(float, 2048, 32, 8, 0, 32, 16, 4);          // v0: 512 thr x 128 regs
   REG_COL(float, 2048, 16, 8, 0, 16, 16, 8);          // v1
-  REG_COL(float, 4096, 16, 4, 0, 16, 16, 16);
+  REG_COL(float, 4096, 16, 4, 0, 16, 16, 16);         // v0: 1024 thr x 64 regs, 32 B runs, 136 KB: 1 CTA/SM
+  REG_COL(float, 4096, 16, 2, 0, 16, 16, 16);         // v1: 512 thr x 64 regs, 16 B runs, 68 KB: 2 CTA/SM
+  REG_COL(float, 4096, 32, 2, 0, 32, 16, 8);          // v2: 256 thr x 128 regs, 16 B runs, 68 KB: 2 CTA/SM
+  REG_COL(float, 4096, 32, 4, 0, 32, 16, 8);          // v3: 512 thr x 128 regs, 32 B runs, 136 KB: 1 CTA/SM
   REG_TRANS(float, 4, 2, 64, 0, 2, 2);
   REG_TRANS(float, 8, 4, 64, 0, 4, 2);
   REG_TRANS(float, 16, 4, 32, 0, 4, 4);

@@ -26,6 +26,10 @@ KernelEntry make_ring_entry() {
 
 void register_ring(void (*add)(const KernelEntry&)) {
   REG_RING(2, 3, double, 4096, 16, 1, 1, 16, 16, 16);    // cfg2: 2 groups x 256 thr, 3 x 68 KB stages
+  // small batches of short rows (cfg1: 4096 rows of c64 N=1024 = 14 tiles per SM): the whole share of an SM is
+  // requested from HBM at kernel start instead of wave by wave
+  REG_RING(4, 12, float, 1024, 16, 2, 1, 16, 16, 4);     // v0: 4 groups x 128 thr, 12 x 17 KB stages
+  REG_RING(8, 24, float, 1024, 16, 1, 1, 16, 16, 4);     // v1: 8 groups x 64 thr, 24 x 8.5 KB stages
   // measured on B200 (profiles/r01_ring_vs_plain.txt): the ring wins only where FP64 + 68 KB tiles leave the plain
   // kernel latency-bound (c128 N=4096: 81.7 % -> 88.4 % of measured HBM peak).  It loses for c128 N=2048
   // (93.0 % vs 96.3 %), c64 N=8192 (73.5 % vs 80.4 %) and c64 N=4096 (81.3 % vs 91.6 %), where the extra

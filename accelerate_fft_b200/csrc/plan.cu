@@ -53,17 +53,19 @@ static void ensure_registry() {
     register_f64_large(add_entry);
     register_f64_col(add_entry);
     register_ring(add_entry);
+    register_pair(add_entry);
     register_fused(add_fused);
   });
 }
 
 // Developer override: B200FFT_VARIANTS="r4096d=1,c1024f=2" picks registration-order variant 1 of the
-// c128 row kernel for N=4096, etc. (flavour r/c/t, N, type f/d).  Default is variant 0.
+// c128 row kernel for N=4096, etc. (flavour r/c/t/g/p = row/col/trans/ring/pair, N, type f/d).  Default is variant 0.
 static int forced_variant(int is_double, int N, int flavor) {
   const char* env = getenv("B200FFT_VARIANTS");
   if (!env) return 0;
   char key[64];
-  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : 't', N, is_double ? 'd' : 'f');
+  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : flavor == FL_RING ? 'g' : flavor == FL_ROWPAIR ? 'p' : 't', N,
+           is_double ? 'd' : 'f');
   const char* p = env;
   while ((p = strstr(p, key)) != nullptr) {
     if (p == env || p[-1] == ',') return atoi(p + strlen(key));
@@ -283,12 +285,17 @@ struct Builder {
     if (ps.ntiles >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return false; }
     char buf[256];
     snprintf(buf, sizeof buf, "%s: lines N=%d v%d E=%d TL=%d minb=%d %s%s radix=%dx%dx%dx%d threads=%d smem=%zu tiles=%lld", what, k->N,
-             k->variant, k->E, k->TL, k->minb, flavor == FL_ROW ? "row" : flavor == FL_COL ? "col" : "trans", tw4 ? "+tw" : "", k->rad[0], k->rad[1],
+             k->variant, k->E, k->TL, k->minb, flavor == FL_ROW ? "row" : flavor == FL_COL ? "col" : flavor == FL_ROWPAIR ? "row+radix2" : "trans",
+             tw4 ? "+tw" : "", k->rad[0], k->rad[1],
              k->rad[2], k->rad[3], k->threads, k->smem, ps.ntiles);
     ps.desc = buf;
     if (flavor == FL_ROW && !tw4 && g.ils == N && g.ols == N && g.ins == 1 && g.ons == 1 && g.nb == 1 && g.no == 1 &&
         !(getenv("B200FFT_NO_RING") && atoi(getenv("B200FFT_NO_RING")))) {
       const KernelEntry* r = find_kernel(p->is_double, N, FL_RING, 0, 0);
+      // short c64 rows: the ring only pays for small batches (the plain kernel streams big ones at ~100 %)
+      // (opt-in via B200FFT_RING_C64_MAX_LINES; measured slower than the plain kernel at every batch size,
+      //  cfg1: 19.7-20.7 us against 16.7 us -- profiles/r01_pair2d_and_narrow_columns.txt)
+      if (r && !p->is_double && g.nl > env_int("B200FFT_RING_C64_MAX_LINES", 0)) r = nullptr;
       // worth it only when every SM gets a few tiles to pipeline
       if (r && (g.nl + r->TL - 1) / r->TL >= 2LL * 148) {
         ps.ring = r;
@@ -477,7 +484,8 @@ struct Builder {
     return fused_pass(fz, ga, gb, fp, 0, true, true, "plane-xy");
   }
 
-  int max_col_n() const { return 2048; }   // longest strided axis done in one pass (>= 64 B runs)
+  // longest strided axis done in one pass (>= 64 B runs)
+  int max_col_n() const { return env_int("B200FFT_MAX_COL_N", 2048); }
   int max_row_n() const { return p->is_double ? 8192 : 16384; }  // largest N with a row kernel
 
   // ---- transform along one axis of an array viewed as [O][N][I] (I = element stride of the axis)
@@ -607,6 +615,43 @@ struct Builder {
       g.tw_div = 1;
       if (!lines_pass((int)N3, FL_TRANS, false, g, 0, false, 0, "6step-C")) { err = B200FFT_INTERNAL_ERROR; return; }
     }
+  }
+
+  // ---- 2D [H][W] with a column length H = 2*M the single-pass column kernel cannot hold: two HBM passes --------
+  // The column axis is split H = 2 x M (n = n1*M + n2, k = k1 + 2*k2).  Pass 1 is the row pass over W with the
+  // radix-2 butterfly over n1 folded into its load: the CTA for (n2, k1) reads rows n2 and n2 + M, transforms
+  // x[n2] + (-1)^k1 x[n2+M] along W, multiplies by w_H^(k1*n2) (one constant per row) and stores row 2*n2 + k1.
+  // Pass 2 is the M-point column transform over n2 of the rows of parity k1, in place (k2 lands on row k1 + 2*k2).
+  bool try_pair_2d(long long H, long long W) {
+    // Opt-in (B200FFT_PAIR2D=1).  Measured on B200 (profiles/r01_pair2d_and_narrow_columns.txt): correct, but the
+    // column pass it needs -- 4096-point columns in tiles only 2-4 columns wide (16-32 B runs) -- reaches just
+    // 2.5 TB/s, so cfg3 takes 693 us with it against 562 us for rows + two wide-tile column passes.
+    if (!(getenv("B200FFT_PAIR2D") && atoi(getenv("B200FFT_PAIR2D")))) return false;
+    if (!is_pow2(H) || !is_pow2(W) || H < 4) return false;
+    const long long M = H / 2;
+    if (H <= max_col_n() || M > env_int("B200FFT_PAIR_MAX_COL_N", 4096)) return false;
+    if (!find_kernel(p->is_double, (int)W, FL_ROWPAIR, 0, 0) || !find_kernel(p->is_double, (int)M, FL_COL, 0, 0)) return false;
+    if (H * W >= (1LL << 40) || M >= (1LL << 30)) return false;
+    {
+      Geom g{};
+      g.nb = 1; g.no = (int)M; g.nl = 2;
+      g.ios = W; g.ils = 0; g.ins = 1; g.pre2_off = M * W;
+      g.oos = 2 * W; g.ols = W; g.ons = 1;
+      g.tw_div = 1;
+      const size_t before = p->passes.size();
+      if (!lines_pass((int)W, FL_ROWPAIR, false, g, 0, false, 0, "pair-rows")) return false;
+      Pass& ps = p->passes[before];
+      make_fourstep_tables(p, H, &ps.g.tw_lo_bits, &ps.tw_lo, &ps.tw_hi);
+    }
+    {
+      Geom g{};
+      g.nb = 1; g.no = 2; g.nl = (int)W;
+      g.ios = W; g.ils = 1; g.ins = 2 * W;
+      g.oos = W; g.ols = 1; g.ons = 2 * W;
+      g.tw_div = 1;
+      if (!lines_pass((int)M, FL_COL, false, g, 0, true, 0, "pair-cols")) { err = B200FFT_INTERNAL_ERROR; return true; }
+    }
+    return true;
   }
 
   // ---- arbitrary (non power-of-two) axis lengths: generic_kernel.cu -----------------------
@@ -752,8 +797,10 @@ int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type) {
   auto* p = new b200fft_plan_s;
   p->is_double = dbl; p->rank = 2; p->dims[0] = h; p->dims[1] = w; p->total = h * w;
   Builder b{p};
-  b.axis(h, w, 1);   // rows
-  b.axis(1, h, w);   // columns
+  if (!b.try_pair_2d(h, w)) {
+    b.axis(h, w, 1);   // rows
+    b.axis(1, h, w);   // columns
+  }
   return finish_plan(p, b, plan);
 }
 

@@ -5,7 +5,8 @@
 
 namespace b200fft {
 
-enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3 };  // FL_RING: persistent TMA-fed rows (ring_kernel.cuh)
+// FL_RING: persistent TMA-fed rows (ring_kernel.cuh); FL_ROWPAIR: rows with the radix-2 pre-butterfly (Geom::pre2_off)
+enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4 };
 
 struct KernelEntry {
   int is_double;
@@ -21,7 +22,6 @@ struct KernelEntry {
   const void* func;
 };
 
-template <class K, bool LLF, bool SLF, bool TW4> KernelEntry make_entry();
 
 // two line-kernel phases fused into one launch (fused_kernel.cuh)
 struct FusedEntry {
@@ -44,5 +44,6 @@ void register_f64_small(void (*add)(const KernelEntry&));
 void register_f64_large(void (*add)(const KernelEntry&));
 void register_f64_col(void (*add)(const KernelEntry&));
 void register_ring(void (*add)(const KernelEntry&));
+void register_pair(void (*add)(const KernelEntry&));
 
 }  // namespace b200fft

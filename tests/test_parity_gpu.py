@@ -150,6 +150,36 @@ def test_fft2d_vs_oracle(af, oracle, dtype, mode):
             assert rel_l2(y, oracle.fft2D(mode, x, threads=4)) <= bar(dtype, x.size), (shape, mode)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_fft2d_two_pass_row_pair_plan(af, oracle, dtype, mode):
+    """Column lengths of 2 x (longest single-pass column) take the two-pass plan: row pass with the radix-2
+    butterfly of rows n2 / n2+H/2 folded into its load, then an in-place H/2-point column pass (plan.cu
+    try_pair_2d).  Checked against numpy in double and, on a 4096 x 1024 problem, against the oracle."""
+    rng = np.random.default_rng(31)
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    os.environ["B200FFT_PAIR2D"] = "1"     # opt-in plan (measured slower than the default on B200, see plan.cu)
+    af.lib().accfft_plan_cache_clear()
+    try:
+        for shape in [(4096, 1024), (4096, 2048), (8192, 1024)]:
+            if dtype == np.complex128 and shape[0] > 4096:
+                continue      # c128 columns of 4096 have no single-pass kernel: that shape keeps the four-step plan
+            p = af.Plan("2d", list(shape), typ, 1)
+            d = p.describe()
+            p.destroy()
+            assert "pair-rows" in d and "pair-cols" in d and len(d.strip().split("\n")) == 2, d
+            x = rand_complex(rng, shape, dtype)
+            y = gpu(af, "fft2D", mode, x)
+            x128 = x.astype(np.complex128)
+            ex = np.fft.fft2(x128) if mode == "Forward" else np.fft.ifft2(x128) * (1 if mode == "Inverse" else x.size)
+            assert rel_l2(y, ex) <= bar(dtype, x.size), (shape, mode)
+            if shape == (4096, 1024):
+                assert rel_l2(y, oracle.fft2D(mode, x, threads=8)) <= bar(dtype, x.size), (shape, mode)
+    finally:
+        os.environ["B200FFT_PAIR2D"] = "0"
+        af.lib().accfft_plan_cache_clear()
+
+
 SHAPES_3D = [(1, 1, 1), (2, 2, 2), (16, 32, 64), (64, 32, 16), (10, 12, 14), (3, 5, 7), (5, 64, 33), (4, 1024, 8), (1024, 4, 8),
              (64, 64, 64), (16, 16, 4096)]
 
