@@ -120,6 +120,39 @@ def run_host(kind, mode, a):
     return out
 
 
+def run_host_seq(kind, modes, h_in, h_out=None):
+    """Chain of transforms over a HOST array through the C ABI (accfft_run_host_seq): copy in, `modes` applied one
+    after the other on the device, copy out; for kind "fft" the rows flow through the device in chunks so both
+    copies overlap the kernels.  h_in / h_out: numpy arrays or CPU torch tensors (pinned for asynchronous DMA)."""
+    import numpy as np
+    torch = None
+    if not isinstance(h_in, np.ndarray):
+        torch = _torch()
+        if h_in.is_cuda:
+            raise RuntimeError("run_host_seq takes host arrays")
+        h_in = h_in.contiguous()
+        if h_out is None:
+            h_out = torch.empty_like(h_in)
+        typ = _type_of(h_in)
+        pin, pout, shp = h_in.data_ptr(), h_out.data_ptr(), tuple(h_in.shape)
+    else:
+        h_in = np.ascontiguousarray(h_in)
+        if h_in.dtype == np.complex64:
+            typ = C2C
+        elif h_in.dtype == np.complex128:
+            typ = Z2Z
+        else:
+            raise TypeError("only complex64 / complex128")
+        if h_out is None:
+            h_out = np.empty_like(h_in)
+        pin, pout, shp = h_in.ctypes.data, h_out.ctypes.data, h_in.shape
+    k = {"fft": 0, "fft1D": 1, "fft2D": 2, "fft3D": 3}[kind]
+    ms = (ctypes.c_int * len(modes))(*[_MODE[m] for m in modes])
+    shape = (ctypes.c_int64 * len(shp))(*shp)
+    _lib.check(lib().accfft_run_host_seq(k, ms, len(modes), len(shp), shape, typ, pin, pout), kind)
+    return h_out
+
+
 def set_fused_inverse(on):
     lib().accfft_set_fused_inverse(1 if on else 0)
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "b200fftPlan1d", "b200fftPlan2d", "b200fftPlan3d", "b200fftPlanMany1d", "b200fftExec",
     "b200fftExecScaled", "b200fftDestroy", "b200fftErrorString", "b200fftScratchBytes",
     "b200fftNumPasses", "b200fftKernelLaunches", "b200fftDescribe",
-    "accfft_fft", "accfft_fft1D", "accfft_fft2D", "accfft_fft3D", "accfft_run_host",
+    "accfft_fft", "accfft_fft1D", "accfft_fft2D", "accfft_fft3D", "accfft_run_host", "accfft_run_host_seq",
     "accfft_set_fused_inverse", "accfft_plan_cache_size", "accfft_plan_cache_clear",
     "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack", "b200fftTrimScratch",
 ]
@@ -77,6 +77,7 @@ def lib():
     L.accfft_fft2D.argtypes = [i, i64, i64, i, vp, vp, vp]
     L.accfft_fft3D.argtypes = [i, i64, i64, i64, i, vp, vp, vp]
     L.accfft_run_host.argtypes = [i, i, i, pi64, i, vp, vp]
+    L.accfft_run_host_seq.argtypes = [i, ctypes.POINTER(ctypes.c_int), i, i, pi64, i, vp, vp]
     L.accfft_set_fused_inverse.argtypes = [i]
     L.accfft_set_fused_inverse.restype = None
     L.accfft_plan_cache_clear.restype = None

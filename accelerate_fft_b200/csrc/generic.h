@@ -43,5 +43,7 @@ cudaError_t launch_copy_scale(int is_double, const void* src, void* dst, long lo
 cudaError_t launch_slab_pack(int is_double, bool pack, const void* src, void* dst, long long dl, long long h, long long w, int P,
                              cudaStream_t stream);
 int generic_set_attrs();
+// stream-ordered allocation from the library-owned scratch pool (plan.cu); release with cudaFreeAsync
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t stream);
 
 }  // namespace b200fft

@@ -152,35 +152,105 @@ int accfft_fft3D(int mode, int64_t d, int64_t h, int64_t w, int type, const void
   return run(fft3D_plans, mode, d, h, w, type, (double)d * (double)h * (double)w, in, out, stream);  // FFT.hs:155
 }
 
-int accfft_run_host(int kind, int mode, int rank, const int64_t* shape, int type, const void* h_in, void* h_out) {
-  if (rank < 1 || rank > 8 || !shape) return B200FFT_INVALID_VALUE;
-  if ((kind == 1 && rank != 1) || (kind == 2 && rank != 2) || (kind == 3 && rank != 3)) return B200FFT_INVALID_VALUE;
+// One whole-array transform (or a chain of them) of a device-resident array on `stream`; src is preserved,
+// the result of the last transform lands in *result (either bufA or bufB, ping-pong).
+static int run_chain(int kind, const int* modes, int nmodes, int rank, const int64_t* shape, int type, const void* src, void* bufA,
+                     void* bufB, b200fftStream stream, void** result) {
+  const void* cur = src;
+  void* dst = bufB;
+  for (int m = 0; m < nmodes; m++) {
+    int e;
+    switch (kind) {
+      case 0: e = accfft_fft(modes[m], rank, shape, type, cur, dst, stream); break;
+      case 1: e = accfft_fft1D(modes[m], shape[0], type, cur, dst, stream); break;
+      case 2: e = accfft_fft2D(modes[m], shape[0], shape[1], type, cur, dst, stream); break;
+      case 3: e = accfft_fft3D(modes[m], shape[0], shape[1], shape[2], type, cur, dst, stream); break;
+      default: e = B200FFT_INVALID_VALUE;
+    }
+    if (e) return e;
+    cur = dst;
+    dst = (dst == bufB) ? bufA : bufB;
+  }
+  *result = const_cast<void*>(cur);
+  return 0;
+}
+
+// Host-buffer flavour: what Accelerate's `run` does around the foreign call (copy the `use`d array in, run the
+// Aforeign nodes, copy the result out), for a chain of `nmodes` transforms applied one after the other
+// (e.g. {Forward, Inverse}) with the array staying on the device in between.
+//
+// B200-first: for kind 0 (`fft`, innermost axis -- the rows are independent units) the array is cut into chunks of
+// whole rows that flow through three streams, so the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy
+// of chunk c-1 overlap (PCIe is full duplex and the copy engines are separate from the SMs); the step then costs
+// max(H2D, D2H) instead of H2D + kernels + D2H.  Device staging comes from the library's scratch pool.  Whole-array
+// transforms (fft1D/2D/3D) cannot be cut and run copy -> transform -> copy.  Synchronous; pass pinned host buffers
+// for asynchronous DMA (pageable memory works but serialises inside the driver).
+int accfft_run_host_seq(int kind, const int* modes, int nmodes, int rank, const int64_t* shape, int type, const void* h_in,
+                        void* h_out) {
+  if (rank < 1 || rank > 8 || !shape || !modes || nmodes < 1 || !h_in || !h_out) return B200FFT_INVALID_VALUE;
+  if ((kind == 1 && rank != 1) || (kind == 2 && rank != 2) || (kind == 3 && rank != 3) || kind < 0 || kind > 3) return B200FFT_INVALID_VALUE;
+  if (type != B200FFT_C2C && type != B200FFT_Z2Z) return B200FFT_INVALID_TYPE;
+  for (int m = 0; m < nmodes; m++) if (modes[m] < Forward || modes[m] > Inverse) return B200FFT_INVALID_VALUE;
   long long n = 1;
-  for (int i = 0; i < rank; i++) n *= shape[i];
+  for (int i = 0; i < rank; i++) { if (shape[i] < 0) return B200FFT_INVALID_SIZE; n *= shape[i]; }
   if (n == 0) return 0;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return B200FFT_NO_DEVICE; }
-  const size_t bytes = (size_t)n * (type == B200FFT_Z2Z ? 16 : 8);
-  void *d_in = nullptr, *d_out = nullptr;
-  if (cudaMalloc(&d_in, bytes) != cudaSuccess) { cudaGetLastError(); return B200FFT_ALLOC_FAILED; }
-  if (cudaMalloc(&d_out, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(d_in); return B200FFT_ALLOC_FAILED; }
-  int e = 0;
-  if (cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) e = B200FFT_EXEC_FAILED;
-  if (!e) {
-    switch (kind) {
-      case 0: e = accfft_fft(mode, rank, shape, type, d_in, d_out, nullptr); break;
-      case 1: e = accfft_fft1D(mode, shape[0], type, d_in, d_out, nullptr); break;
-      case 2: e = accfft_fft2D(mode, shape[0], shape[1], type, d_in, d_out, nullptr); break;
-      case 3: e = accfft_fft3D(mode, shape[0], shape[1], shape[2], type, d_in, d_out, nullptr); break;
-      default: e = B200FFT_INVALID_VALUE;
-    }
+  const size_t esz = type == B200FFT_Z2Z ? 16 : 8;
+  const size_t bytes = (size_t)n * esz;
+  const int64_t w = shape[rank - 1];
+  const int64_t outer = n / w;
+
+  // chunking: ~64 MiB chunks, at least 4 of them, whole rows each
+  int64_t rows_per_chunk = outer;
+  constexpr int NSLOT = 3;
+  if (kind == 0 && outer >= 2 * NSLOT && bytes >= ((size_t)32 << 20)) {
+    int64_t nchunks = (int64_t)(bytes >> 26);
+    if (nchunks < 2 * NSLOT) nchunks = 2 * NSLOT;
+    if (nchunks > outer) nchunks = outer;
+    rows_per_chunk = (outer + nchunks - 1) / nchunks;
   }
-  if (!e && cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, 0) != cudaSuccess) e = B200FFT_EXEC_FAILED;
-  if (cudaStreamSynchronize(0) != cudaSuccess && !e) e = B200FFT_EXEC_FAILED;
-  cudaFree(d_in);
-  cudaFree(d_out);
+  const int64_t nchunks = (outer + rows_per_chunk - 1) / rows_per_chunk;
+  const int nslot = nchunks > 1 ? NSLOT : 1;
+  const size_t chunk_bytes = (size_t)rows_per_chunk * w * esz;
+
+  cudaStream_t st[NSLOT] = {nullptr, nullptr, nullptr};
+  void *a[NSLOT] = {nullptr, nullptr, nullptr}, *b[NSLOT] = {nullptr, nullptr, nullptr};
+  int e = 0;
+  for (int s = 0; s < nslot && !e; s++) {
+    if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess) { e = B200FFT_ALLOC_FAILED; break; }
+    if (b200fft::pool_alloc(&a[s], chunk_bytes, st[s]) != cudaSuccess || b200fft::pool_alloc(&b[s], chunk_bytes, st[s]) != cudaSuccess)
+      e = B200FFT_ALLOC_FAILED;
+  }
+  for (int64_t c = 0; c < nchunks && !e; c++) {
+    const int s = (int)(c % nslot);
+    const int64_t r0 = c * rows_per_chunk;
+    const int64_t rows = (outer - r0 < rows_per_chunk) ? outer - r0 : rows_per_chunk;
+    const size_t off = (size_t)r0 * w * esz, cb = (size_t)rows * w * esz;
+    if (cudaMemcpyAsync(a[s], (const char*)h_in + off, cb, cudaMemcpyHostToDevice, st[s]) != cudaSuccess) { e = B200FFT_EXEC_FAILED; break; }
+    void* res = nullptr;
+    if (nchunks == 1) {
+      e = run_chain(kind, modes, nmodes, rank, shape, type, a[s], a[s], b[s], st[s], &res);
+    } else {
+      const int64_t sh2[2] = {rows, w};   // a chunk of rows is a DIM2 array for `fft` (same innermost length, same scale)
+      e = run_chain(0, modes, nmodes, 2, sh2, type, a[s], a[s], b[s], st[s], &res);
+    }
+    if (e) break;
+    if (cudaMemcpyAsync((char*)h_out + off, res, cb, cudaMemcpyDeviceToHost, st[s]) != cudaSuccess) e = B200FFT_EXEC_FAILED;
+  }
+  for (int s = 0; s < nslot; s++) {
+    if (!st[s]) continue;
+    if (a[s]) cudaFreeAsync(a[s], st[s]);
+    if (b[s]) cudaFreeAsync(b[s], st[s]);
+    if (cudaStreamSynchronize(st[s]) != cudaSuccess && !e) e = B200FFT_EXEC_FAILED;
+    cudaStreamDestroy(st[s]);
+  }
   if (e) cudaGetLastError();
   return e;
+}
+
+int accfft_run_host(int kind, int mode, int rank, const int64_t* shape, int type, const void* h_in, void* h_out) {
+  return accfft_run_host_seq(kind, &mode, 1, rank, shape, type, h_in, h_out);
 }
 
 void accfft_set_fused_inverse(int on) { g_fused_inverse = on != 0; }

@@ -136,6 +136,8 @@ static cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
   if (!pool) return cudaErrorMemoryAllocation;
   return cudaMallocFromPoolAsync(p, bytes, pool, s);
 }
+// the host-buffer entry points (host_api.cu) stage their chunks in the same pool
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t s) { return scratch_alloc(p, bytes, s); }
 
 // ------------------------------------------------------------------------------------------
 // plan representation

@@ -108,6 +108,12 @@ int accfft_fft3D(int mode, int64_t d, int64_t h, int64_t w, int type, const void
 /* ... and host-buffer flavour (what `run` does around it): H2D copy, transform, D2H copy,
  * synchronous.  kind: 0 fft (innermost axis), 1 fft1D, 2 fft2D, 3 fft3D. */
 int accfft_run_host(int kind, int mode, int rank, const int64_t* shape, int type, const void* h_in, void* h_out);
+/* Same for a chain of `nmodes` transforms applied one after the other with the array staying on the device in
+ * between (e.g. {0, 2} = Inverse . Forward) -- one Accelerate `run` holding several Aforeign nodes.  For kind 0
+ * the rows are independent, so the array flows through the device in chunks of whole rows on three streams:
+ * H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 overlap.  Pass pinned host buffers. */
+int accfft_run_host_seq(int kind, const int* modes, int nmodes, int rank, const int64_t* shape, int type,
+                        const void* h_in, void* h_out);
 /* when set non-zero the Inverse scale is fused into the last pass instead of a second kernel */
 void accfft_set_fused_inverse(int on);
 int accfft_plan_cache_size(void);

@@ -62,6 +62,9 @@ def test_no_cpu_fallback(af):
     with pytest.raises(af.B200FFTError) as ei:
         af.run_host("fft", "Forward", np.ones((2, 8), np.complex64))
     assert ei.value.status == 11
+    with pytest.raises(af.B200FFTError) as ei:
+        af.run_host_seq("fft", ["Forward", "Inverse"], np.ones((2, 8), np.complex64))
+    assert ei.value.status == 11
     with pytest.raises(RuntimeError):
         af.fft("Forward", torch.ones(8, dtype=torch.complex64))
     h = ctypes.c_void_p()

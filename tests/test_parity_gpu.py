@@ -244,6 +244,31 @@ def test_host_buffer_entry_and_fused_inverse(af, oracle):
         af.set_fused_inverse(False)
 
 
+def test_host_chain_pipelined_in_row_chunks(af, oracle):
+    """accfft_run_host_seq: a chain of transforms over a HOST array; for `fft` the rows flow through the device in
+    chunks on three streams (>= 32 MiB arrays).  A chunk of rows runs the same kernel as the whole array, so the
+    result must equal the device-resident path bit for bit; a sample of rows is checked against the oracle."""
+    import torch
+    rng = np.random.default_rng(23)
+    for dtype, shape in ((np.complex64, (8200, 1024)), (np.complex128, (3, 1030, 1024))):   # 64 MiB / 48 MiB, ragged last chunk
+        x = rand_complex(rng, shape, dtype)
+        hx = torch.from_numpy(x).pin_memory()
+        y = af.run_host_seq("fft", ["Forward"], hx).numpy()
+        yd = af.fft("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.array_equal(y, yd)
+        rows = x.reshape(-1, 1024)[::97]
+        assert rel_l2(y.reshape(-1, 1024)[::97], oracle.fft("Forward", rows)) <= bar(dtype, 1024)
+        z = af.run_host_seq("fft", ["Forward", "Inverse"], x)           # pageable numpy buffers work too
+        assert rel_l2(z, x) <= 2 * bar(dtype, 1024)
+        z2 = af.fft("Inverse", af.fft("Forward", torch.from_numpy(x).cuda())).cpu().numpy()
+        assert np.array_equal(z, z2)
+    # whole-array kinds and small arrays take the unchunked route
+    x2 = rand_complex(rng, (64, 48), np.complex64)
+    assert rel_l2(af.run_host_seq("fft2D", ["Forward", "Reverse"], x2), x2.astype(np.complex128) * x2.size) <= 2 * bar(np.complex64, x2.size)
+    with pytest.raises(af.B200FFTError):
+        af.run_host_seq("fft2D", ["Forward"], np.ones((2, 3, 4), np.complex64))
+
+
 def test_plan_cache_and_streams(af):
     """Plans are cached per (context, shape, type) (PTX/Plans.hs:66-86) and exec takes the stream as an argument."""
     import torch
