@@ -54,17 +54,18 @@ static void ensure_registry() {
     register_f64_col(add_entry);
     register_ring(add_entry);
     register_pair(add_entry);
+    register_cluster(add_entry);
     register_fused(add_fused);
   });
 }
 
 // Developer override: B200FFT_VARIANTS="r4096d=1,c1024f=2" picks registration-order variant 1 of the
-// c128 row kernel for N=4096, etc. (flavour r/c/t/g/p = row/col/trans/ring/pair, N, type f/d).  Default is variant 0.
+// c128 row kernel for N=4096, etc. (flavour r/c/t/g/p/k = row/col/trans/ring/pair/cluster, N, type f/d).  Default is variant 0.
 static int forced_variant(int is_double, int N, int flavor) {
   const char* env = getenv("B200FFT_VARIANTS");
   if (!env) return 0;
   char key[64];
-  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : flavor == FL_RING ? 'g' : flavor == FL_ROWPAIR ? 'p' : 't', N,
+  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : flavor == FL_RING ? 'g' : flavor == FL_ROWPAIR ? 'p' : flavor == FL_CLUSTER ? 'k' : 't', N,
            is_double ? 'd' : 'f');
   const char* p = env;
   while ((p = strstr(p, key)) != nullptr) {
@@ -144,7 +145,7 @@ cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t s) { return scratch_
 // ------------------------------------------------------------------------------------------
 enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3, PK_FUSED2 = 4 };
+enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3, PK_FUSED2 = 4, PK_CLUSTER = 5 };
 
 struct Pass {
   int kind = PK_LINES;
@@ -158,6 +159,7 @@ struct Pass {
   void* tws = nullptr;             // device: stage twiddles
   void* tw_lo = nullptr;           // device: four-step twiddle tables
   void* tw_hi = nullptr;
+  void* ctw = nullptr;             // PK_CLUSTER: inner twiddles w_N^(k1*r), [CS-1][N1]
   long long ntiles = 0;
   const FusedEntry* fz = nullptr;  // PK_FUSED2
   FusedParams fp{};
@@ -310,6 +312,47 @@ struct Builder {
     return true;
   }
 
+
+  // ---- one launch of a cluster (DSMEM) column kernel: strided axis [O][N][I] in place, N = N1*CS ------
+  static int cluster_min_n() { return env_int("B200FFT_CLUSTER_MIN_N", 4096); }
+  bool cluster_pass(long long O, long long N, long long I, const char* what) {
+    if (getenv("B200FFT_NO_CLUSTER") && atoi(getenv("B200FFT_NO_CLUSTER"))) return false;
+    if (N < cluster_min_n() || N >= (1LL << 30)) return false;
+    const KernelEntry* k = find_kernel(p->is_double, (int)N, FL_CLUSTER, 0, 0);
+    if (!k) return false;
+    const long long esz = p->is_double ? 16 : 8, tpt = k->N1 / k->E;
+    if (tpt * k->CS * I * esz >= (1LL << 32)) return false;
+    Pass ps;
+    ps.kind = PK_CLUSTER;
+    ps.k = k;
+    Geom g{};
+    g.nb = 1; g.no = (int)O; g.nl = (int)I;
+    g.ios = N * I; g.ils = 1; g.ins = I;
+    g.oos = N * I; g.ols = 1; g.ons = I;
+    g.tw_div = 1;
+    g.ntl = (g.nl + k->TL - 1) / k->TL;
+    ps.g = g;
+    ps.inplace_ok = true;
+    ps.ntiles = (long long)O * g.ntl;
+    if (ps.ntiles * k->CS >= (1LL << 31)) return false;
+    ps.tws = make_stage_twiddles(p, k);
+    {  // inner four-step twiddles w_N^(k1 * r), r = 1 .. CS-1, k1 < N1
+      auto build = [&](auto tag) -> void* {
+        using T = decltype(tag);
+        std::vector<T> h(2 * (size_t)(k->CS - 1) * k->N1);
+        for (int r = 1; r < k->CS; r++)
+          for (int k1 = 0; k1 < k->N1; k1++) fill_root_table(h, (size_t)(r - 1) * k->N1 + k1, (long long)r * k1, N);
+        return upload(p, h);
+      };
+      ps.ctw = p->is_double ? build(double{}) : build(float{});
+    }
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: cluster cols N=%d=%dx%d v%d E=%d TL=%d minb=%d radix=%dx%dx%dx%d | %d threads=%d smem=%zu clusters=%lld", what, k->N,
+             k->N1, k->CS, k->variant, k->E, k->TL, k->minb, k->rad[0], k->rad[1], k->rad[2], k->rad[3], k->CS, k->threads, k->smem, ps.ntiles);
+    ps.desc = buf;
+    push(ps);
+    return true;
+  }
 
   // ---- two phases in one launch with an L2-resident intermediate (fused_kernel.cuh) -----------
   static size_t counters_bytes(int nbands) { return (((size_t)(1 + 2 * nbands) * 4) + 255) / 256 * 256; }
@@ -517,6 +560,7 @@ struct Builder {
       if (!lines_pass((int)N, FL_COL, false, g, 0, true, 0, "cols")) err = B200FFT_INTERNAL_ERROR;
       return;
     }
+    if (cluster_pass(O, N, I, "cols")) return;
     fourstep_strided(O, N, I);
   }
 
@@ -704,6 +748,14 @@ static int set_func_attrs(b200fft_plan_s* p) {
       if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess)
         return B200FFT_INTERNAL_ERROR;
     }
+    if (ps.kind == PK_CLUSTER) {
+      if (ps.k->smem > 48 * 1024 &&
+          cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess)
+        return B200FFT_INTERNAL_ERROR;
+      if (ps.k->CS > 8 && cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+        return B200FFT_INTERNAL_ERROR;
+      cudaFuncSetAttribute(ps.k->func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if (ps.kind == PK_FUSED2) {
       if (ps.fz->smem > 48 * 1024 &&
           cudaFuncSetAttribute(ps.fz->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.fz->smem) != cudaSuccess)
@@ -867,6 +919,25 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
       } else {
         ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
       }
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (ps.kind == PK_CLUSTER) {
+      Geom g = ps.g;
+      g.swap_in = inverse && first;
+      g.swap_out = inverse && last;
+      float scf = (float)sc;
+      double scd = sc;
+      void* args[] = {&g, (void*)&src, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                      p->is_double ? (void*)&scd : (void*)&scf, (void*)&ps.ctw};
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(ps.ntiles * ps.k->CS));
+      cfg.blockDim = dim3(ps.k->threads);
+      cfg.dynamicSmemBytes = ps.k->smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)ps.k->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      ce = cudaLaunchKernelExC(&cfg, ps.k->func, args);
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (ps.kind == PK_FUSED2) {
       FusedParams fp = ps.fp;

@@ -6,7 +6,8 @@
 namespace b200fft {
 
 // FL_RING: persistent TMA-fed rows (ring_kernel.cuh); FL_ROWPAIR: rows with the radix-2 pre-butterfly (Geom::pre2_off)
-enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4 };
+// FL_CLUSTER: strided lines of length N = N1*CS transformed by a cluster of CS CTAs (cluster_kernel.cuh)
+enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4, FL_CLUSTER = 5 };
 
 struct KernelEntry {
   int is_double;
@@ -19,6 +20,7 @@ struct KernelEntry {
   int S, rad[4];
   int tw_len;      // stage twiddle table length (complex elements)
   int G, NS;       // FL_RING: thread groups per CTA, stage buffers
+  int CS, N1;      // FL_CLUSTER: cluster size and per-CTA sub-length (N = N1*CS; S, rad, tw_len describe N1)
   const void* func;
 };
 
@@ -45,5 +47,6 @@ void register_f64_large(void (*add)(const KernelEntry&));
 void register_f64_col(void (*add)(const KernelEntry&));
 void register_ring(void (*add)(const KernelEntry&));
 void register_pair(void (*add)(const KernelEntry&));
+void register_cluster(void (*add)(const KernelEntry&));
 
 }  // namespace b200fft
