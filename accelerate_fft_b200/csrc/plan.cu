@@ -55,17 +55,18 @@ static void ensure_registry() {
     register_ring(add_entry);
     register_pair(add_entry);
     register_cluster(add_entry);
+    register_pipe(add_entry);
     register_fused(add_fused);
   });
 }
 
 // Developer override: B200FFT_VARIANTS="r4096d=1,c1024f=2" picks registration-order variant 1 of the
-// c128 row kernel for N=4096, etc. (flavour r/c/t/g/p/k = row/col/trans/ring/pair/cluster, N, type f/d).  Default is variant 0.
+// c128 row kernel for N=4096, etc. (flavour r/c/t/g/p/k/q = row/col/trans/ring/pair/cluster/pipe, N, type f/d).  Default is variant 0.
 static int forced_variant(int is_double, int N, int flavor) {
   const char* env = getenv("B200FFT_VARIANTS");
   if (!env) return 0;
   char key[64];
-  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : flavor == FL_RING ? 'g' : flavor == FL_ROWPAIR ? 'p' : flavor == FL_CLUSTER ? 'k' : 't', N,
+  snprintf(key, sizeof key, "%c%d%c=", flavor == FL_ROW ? 'r' : flavor == FL_COL ? 'c' : flavor == FL_RING ? 'g' : flavor == FL_ROWPAIR ? 'p' : flavor == FL_CLUSTER ? 'k' : flavor == FL_PIPE ? 'q' : 't', N,
            is_double ? 'd' : 'f');
   const char* p = env;
   while ((p = strstr(p, key)) != nullptr) {
@@ -160,6 +161,11 @@ struct Pass {
   void* tw_lo = nullptr;           // device: four-step twiddle tables
   void* tw_hi = nullptr;
   void* ctw = nullptr;             // PK_CLUSTER: inner twiddles w_N^(k1*r), [CS-1][N1]
+  // persistent software-pipelined alternative of a column pass (pipe_kernel.cuh); needs 16-byte aligned buffers
+  const KernelEntry* pipe = nullptr;
+  void* ptws = nullptr;            // its stage twiddles and inner twiddles
+  void* pctw = nullptr;
+  int pipe_ntl = 0, pipe_grid = 0;
   long long ntiles = 0;
   const FusedEntry* fz = nullptr;  // PK_FUSED2
   FusedParams fp{};
@@ -308,10 +314,47 @@ struct Builder {
         ps.desc += buf;
       }
     }
+    if (flavor == FL_COL) attach_pipe(ps, N, tw4);
     push(ps);
     return true;
   }
 
+
+  // inner four-step twiddles of a cluster kernel: w_N^(k1 * r), r = 1 .. CS-1, k1 < N1
+  void* make_cluster_twiddles(const KernelEntry* k) {
+    if (k->CS <= 1) return nullptr;
+    const long long N = (long long)k->N1 * k->CS;
+    auto build = [&](auto tag) -> void* {
+      using T = decltype(tag);
+      std::vector<T> h(2 * (size_t)(k->CS - 1) * k->N1);
+      for (int r = 1; r < k->CS; r++)
+        for (int k1 = 0; k1 < k->N1; k1++) fill_root_table(h, (size_t)(r - 1) * k->N1 + k1, (long long)r * k1, N);
+      return upload(p, h);
+    };
+    return p->is_double ? build(double{}) : build(float{});
+  }
+
+  // Attach the persistent pipelined kernel to a column pass over [O][N][I] whose Geom is ps.g (ils == ols == 1).
+  void attach_pipe(Pass& ps, long long N, bool tw4) {
+    if (getenv("B200FFT_NO_PIPE") && atoi(getenv("B200FFT_NO_PIPE"))) return;
+    const KernelEntry* q = find_kernel(p->is_double, (int)N, FL_PIPE, tw4 ? 1 : 0, 0);
+    if (!q) return;
+    const Geom& g = ps.g;
+    const long long esz = p->is_double ? 16 : 8;
+    if (g.ils != 1 || g.ols != 1 || g.nl % q->TL) return;
+    // every tile row must start on a 16-byte boundary (cp.async 16) and the kernels use 32-bit byte offsets per tile
+    if ((g.ins * esz) % 16 || (g.ios * esz) % 16 || (g.ibs * esz) % 16) return;
+    if (g.ins * esz * N >= (1LL << 32) || g.ons * esz * N >= (1LL << 32)) return;
+    const long long ntl = g.nl / q->TL, ntiles = (long long)g.nb * g.no * ntl;
+    if (ntiles >= (1LL << 31) / 16 || ntiles < env_int("B200FFT_PIPE_MIN_TILES", 2 * 148 / q->CS)) return;
+    ps.pipe = q;
+    ps.pipe_ntl = (int)ntl;
+    ps.ptws = make_stage_twiddles(p, q);
+    ps.pctw = make_cluster_twiddles(q);
+    char buf[200];
+    snprintf(buf, sizeof buf, " | pipe: N=%dx%d E=%d TL=%d threads=%d smem=%zu tiles=%lld", q->N1, q->CS, q->E, q->TL, q->threads, q->smem, ntiles);
+    ps.desc += buf;
+  }
 
   // ---- one launch of a cluster (DSMEM) column kernel: strided axis [O][N][I] in place, N = N1*CS ------
   static int cluster_min_n() { return env_int("B200FFT_CLUSTER_MIN_N", 4096); }
@@ -336,20 +379,12 @@ struct Builder {
     ps.ntiles = (long long)O * g.ntl;
     if (ps.ntiles * k->CS >= (1LL << 31)) return false;
     ps.tws = make_stage_twiddles(p, k);
-    {  // inner four-step twiddles w_N^(k1 * r), r = 1 .. CS-1, k1 < N1
-      auto build = [&](auto tag) -> void* {
-        using T = decltype(tag);
-        std::vector<T> h(2 * (size_t)(k->CS - 1) * k->N1);
-        for (int r = 1; r < k->CS; r++)
-          for (int k1 = 0; k1 < k->N1; k1++) fill_root_table(h, (size_t)(r - 1) * k->N1 + k1, (long long)r * k1, N);
-        return upload(p, h);
-      };
-      ps.ctw = p->is_double ? build(double{}) : build(float{});
-    }
+    ps.ctw = make_cluster_twiddles(k);
     char buf[256];
     snprintf(buf, sizeof buf, "%s: cluster cols N=%d=%dx%d v%d E=%d TL=%d minb=%d radix=%dx%dx%dx%d | %d threads=%d smem=%zu clusters=%lld", what, k->N,
              k->N1, k->CS, k->variant, k->E, k->TL, k->minb, k->rad[0], k->rad[1], k->rad[2], k->rad[3], k->CS, k->threads, k->smem, ps.ntiles);
     ps.desc = buf;
+    attach_pipe(ps, N, false);
     push(ps);
     return true;
   }
@@ -754,7 +789,37 @@ static int set_func_attrs(b200fft_plan_s* p) {
         return B200FFT_INTERNAL_ERROR;
       if (ps.k->CS > 8 && cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
         return B200FFT_INTERNAL_ERROR;
-      cudaFuncSetAttribute(ps.k->func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      // (the default shared-memory carveout is kept: asking for the maximum shrinks the L1 that stages the in-flight
+      //  global loads -- measured 377 -> 449 us on the 8192-point c64 column pass)
+    }
+    if (ps.pipe) {
+      const KernelEntry* q = ps.pipe;
+      int dev = 0, nsm = 0, nclus = 0;
+      bool ok = cudaFuncSetAttribute(q->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem) == cudaSuccess &&
+                (q->CS <= 8 || cudaFuncSetAttribute(q->func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) &&
+                cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+      if (ok) {
+        if (q->CS > 1) {
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3((unsigned)(nsm / q->CS * q->CS));
+          cfg.blockDim = dim3(q->threads);
+          cfg.dynamicSmemBytes = q->smem;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = (unsigned)q->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          ok = cudaOccupancyMaxActiveClusters(&nclus, q->func, &cfg) == cudaSuccess && nclus > 0;
+        } else {
+          int occ = 0;
+          ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q->func, q->threads, q->smem) == cudaSuccess && occ > 0;
+          nclus = nsm * occ;
+        }
+      }
+      if (!ok) { cudaGetLastError(); ps.pipe = nullptr; }   // the plain kernel still serves the pass
+      else {
+        const long long ntiles = (long long)ps.g.nb * ps.g.no * ps.pipe_ntl;
+        ps.pipe_grid = (int)((nclus < ntiles ? nclus : ntiles) * q->CS);
+      }
     }
     if (ps.kind == PK_FUSED2) {
       if (ps.fz->smem > 48 * 1024 &&
@@ -905,7 +970,27 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
     const bool first = i == 0, last = i + 1 == np;
     const double sc = last ? scale : 1.0;
     cudaError_t ce = cudaSuccess;
-    if (ps.kind == PK_LINES) {
+    if (ps.pipe && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      Geom g = ps.g;
+      g.swap_in = inverse && first;
+      g.swap_out = inverse && last;
+      g.ntl = ps.pipe_ntl;
+      float scf = (float)sc;
+      double scd = sc;
+      void* args[] = {&g, (void*)&src, (void*)&dst, (void*)&ps.ptws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                      p->is_double ? (void*)&scd : (void*)&scf, (void*)&ps.pctw};
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)ps.pipe_grid);
+      cfg.blockDim = dim3(ps.pipe->threads);
+      cfg.dynamicSmemBytes = ps.pipe->smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)ps.pipe->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = ps.pipe->CS > 1 ? 1 : 0;
+      ce = cudaLaunchKernelExC(&cfg, ps.pipe->func, args);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (ps.kind == PK_LINES) {
       Geom g = ps.g;
       g.swap_in = inverse && first;
       g.swap_out = inverse && last;
