@@ -81,7 +81,8 @@ __device__ __forceinline__ constexpr int addr_ct(int ic) {
 }
 
 // One register stage: E/R butterflies of radix R per thread.
-template <class K, int s, typename C>
+// LDG: the twiddle table is in global memory (read through the non-coherent path); false = shared memory
+template <class K, int s, typename C, bool LDG = true>
 __device__ __forceinline__ void run_stage(C (&v)[K::E], int t, const C* __restrict__ tws) {
   constexpr int R = K::rad[s], B = K::E / R, Ns = K::ns(s);
   // twiddle index k = (t + b*TPT) & (Ns-1): thread part + compile-time part
@@ -94,7 +95,8 @@ __device__ __forceinline__ void run_stage(C (&v)[K::E], int t, const C* __restri
       constexpr int kc = (Ns <= K::TPT) ? 0 : ((b * K::TPT) & (Ns - 1));
       static_for<1, R>([&](auto rc) {
         constexpr int r = rc;
-        a[r] = cmul(a[r], __ldg(tp0 + kc + (r - 1) * Ns));
+        if constexpr (LDG) a[r] = cmul(a[r], __ldg(tp0 + kc + (r - 1) * Ns));
+        else a[r] = cmul(a[r], tp0[kc + (r - 1) * Ns]);
       });
     }
     dft<R>(a);

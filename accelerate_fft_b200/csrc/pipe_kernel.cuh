@@ -37,7 +37,7 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -83,7 +83,12 @@ struct PipeCfg {
   static constexpr int EQ = K::E / NQ_;                                  // registers fed by one part
   static constexpr int XCH_ELEMS = (K::COL_ELEMS > TILE_ELEMS) ? K::COL_ELEMS : TILE_ELEMS;
   static constexpr size_t XCH_BYTES = (((size_t)XCH_ELEMS * K::ESZ + 127) / 128) * 128;
-  static constexpr size_t SMEM = (size_t)TILE_BYTES + G * XCH_BYTES + 8 * (NQ_ + 2 * G) + 16;
+  // the stage twiddles and this rank's row of inner twiddles live in shared memory for the life of the CTA: their
+  // global loads queued behind the cp.async stream in the LSU (lg_throttle 22 % of the stall samples)
+  static constexpr int TW_ELEMS = K::TW_LEN + (CS_ > 1 ? K::N : 0);
+  static constexpr size_t TW_BYTES = (((size_t)TW_ELEMS * K::ESZ + 127) / 128) * 128;
+  static constexpr size_t BAR_OFF = (size_t)TILE_BYTES + G * XCH_BYTES + TW_BYTES;
+  static constexpr size_t SMEM = BAR_OFF + 8 * (NQ_ + 2 * G) + 16;
   static_assert(K::S >= 2, "needs at least one shared-memory exchange");
   static_assert(K::E % CS_ == 0 && K::E % NQ_ == 0, "E must split over the cluster and over the landing parts");
   static_assert((K::TL * K::ESZ) % 16 == 0 && PART_CHUNKS % K::THREADS == 0 && K::THREADS % ROW_CHUNKS == 0, "cp.async tiling");
@@ -104,7 +109,8 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
   constexpr int CS = P::CS, NQ = P::NQ, EQ = P::EQ;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* land = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P::TILE_BYTES + P::G * P::XCH_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P::BAR_OFF);
+  C* stw = reinterpret_cast<C*>(smem_raw + P::TILE_BYTES + P::G * P::XCH_BYTES);   // stage twiddles, then inner twiddles
   uint64_t* full = bars;                 // [NQ]  landing part q holds the current tile
   uint64_t* ready = bars + NQ;           // [G]   CS > 1: every CTA of the cluster has drained its exchange buffer g
   uint64_t* landed = bars + NQ + P::G;   // [G]   CS > 1: the exchanged values for group g have arrived here
@@ -119,6 +125,10 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
   const int nk = (q0 < ntiles) ? (int)((ntiles - q0 + nclus - 1) / nclus) : 0;   // tiles of this CTA: q0 + j*nclus
   C* xch = reinterpret_cast<C*>(smem_raw + P::TILE_BYTES + (size_t)grp * P::XCH_BYTES);
 
+  for (int i = threadIdx.x; i < K::TW_LEN; i += P::THREADS) stw[i] = tws[i];
+  if constexpr (CS > 1)
+    if (rank != 0)
+      for (int i = threadIdx.x; i < K::N; i += P::THREADS) stw[K::TW_LEN + i] = ctw[(size_t)(rank - 1) * K::N + i];
   if (threadIdx.x == 0) {
     for (int q = 0; q < NQ; q++) mbar_init(&full[q], K::THREADS);
     for (int i = 0; i < P::G; i++) { mbar_init(&ready[i], CS); mbar_init(&landed[i], 1); }
@@ -186,19 +196,19 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
 
     // ---- phase 1: N1-point transform in this group's exchange buffer -----------------------------------
     if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
-    run_stage<K, 0>(v, t, tws);
+    run_stage<K, 0, C, false>(v, t, stw);
     scatter<K, 0, true>(v, xch, l, t);
     static_for<1, K::S - 1>([&](auto sc) {
       constexpr int s = sc;
       group_bar(gbar, K::THREADS);
       gather<K, true>(v, xch, l, t);
-      run_stage<K, s>(v, t, tws);
+      run_stage<K, s, C, false>(v, t, stw);
       group_bar(gbar, K::THREADS);
       scatter<K, s, true>(v, xch, l, t);
     });
     group_bar(gbar, K::THREADS);
     gather<K, true>(v, xch, l, t);
-    run_stage<K, K::S - 1>(v, t, tws);    // v[e] = output k1 = t + e*TPT of this CTA's N1-point transform
+    run_stage<K, K::S - 1, C, false>(v, t, stw);    // v[e] = output k1 = t + e*TPT of this CTA's N1-point transform
 
     if constexpr (CS == 1) {
       const unsigned step_b = (unsigned)((long long)K::TPT * g.ons * (long long)sizeof(C));
@@ -233,12 +243,12 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
       if (tid < CS) mbar_arrive_remote(map_to_rank(smem_u32(&ready[grp]), (unsigned)tid));
       // inner four-step twiddle w_N^(k1 * rank): anchors from ctw[rank-1][k1] + running product (<= 8 ulp)
       if (rank != 0) {
-        const C* wp = ctw + (size_t)(rank - 1) * K::N;
+        const C* wp = stw + K::TW_LEN;
         constexpr int CH = (K::E < 8) ? K::E : 8;
-        const C stepw = __ldg(wp + K::TPT);
+        const C stepw = wp[K::TPT];
         static_for<0, K::E / CH>([&](auto qc) {
           constexpr int q = qc;
-          C w = __ldg(wp + t + q * CH * K::TPT);
+          C w = wp[t + q * CH * K::TPT];
           static_for<0, CH>([&](auto rc) {
             constexpr int e = q * CH + rc;
             v[e] = cmul(v[e], w);
@@ -247,7 +257,7 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
         });
       }
       // ---- exchange: register e goes to CTA e / EP, slot [rank][(e % EP)*TPT + t][l] of ITS buffer `grp` ----
-      mbar_wait_cluster(&ready[grp], par);
+      mbar_wait(&ready[grp], par);
       {
         const uint32_t base = smem_u32(xch) + (uint32_t)(((int)rank * KL + t) * K::TL + l) * (uint32_t)sizeof(C);
         const uint32_t lbar = smem_u32(&landed[grp]);
@@ -261,7 +271,7 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
           });
         });
       }
-      mbar_wait_cluster(&landed[grp], par);
+      mbar_wait(&landed[grp], par);
 
       // ---- phase 2: radix-CS butterflies over n2 for k1 = rank*KL + t + jj*TPT, rows k1 + N1*k2 ------------
       const C* gp = xch + t * K::TL + l;

@@ -5,6 +5,8 @@ import numpy as np
 import torch
 sys.path.insert(0, ".")
 import accelerate_fft_b200 as af
+os.environ.setdefault("B200FFT_CLUSTER", "1")   # the cluster kernels are opt-in
+os.environ.setdefault("B200FFT_PIPE", "0")
 
 PEAK = 6462.4
 rng = np.random.default_rng(3)
@@ -61,18 +63,18 @@ if "parity" in sys.argv or len(sys.argv) == 1:
 if "time" in sys.argv or len(sys.argv) == 1:
     for v in range(7):
         timing("col 8192 x 8192 c64 cluster v%d" % v, "axis", (1, 8192, 8192), af.C2C, env={"B200FFT_VARIANTS": "k8192f=%d" % v})
-    timing("col 8192 x 8192 c64 four-step (2 passes)", "axis", (1, 8192, 8192), af.C2C, env={"B200FFT_NO_CLUSTER": "1"})
+    timing("col 8192 x 8192 c64 four-step (2 passes)", "axis", (1, 8192, 8192), af.C2C, env={"B200FFT_CLUSTER": "0"})
     timing("rows 8192 x 8192 c64", "many", (8192,), af.C2C) if False else None
     for v in range(5):
         timing("cfg3 2D 8192^2 cluster v%d" % v, "2d", (8192, 8192), af.C2C, env={"B200FFT_VARIANTS": "k8192f=%d" % v})
-    timing("cfg3 2D 8192^2 no cluster", "2d", (8192, 8192), af.C2C, env={"B200FFT_NO_CLUSTER": "1"})
+    timing("cfg3 2D 8192^2 no cluster", "2d", (8192, 8192), af.C2C, env={"B200FFT_CLUSTER": "0"})
     for v in range(2):
         timing("col 4096 x 8192 c64 cluster v%d" % v, "axis", (1, 4096, 8192), af.C2C, env={"B200FFT_VARIANTS": "k4096f=%d" % v})
-    timing("col 4096 x 8192 c64 four-step", "axis", (1, 4096, 8192), af.C2C, env={"B200FFT_NO_CLUSTER": "1"})
+    timing("col 4096 x 8192 c64 four-step", "axis", (1, 4096, 8192), af.C2C, env={"B200FFT_CLUSTER": "0"})
     for v in range(2):
         timing("col 16384 x 4096 c64 cluster v%d" % v, "axis", (1, 16384, 4096), af.C2C, env={"B200FFT_VARIANTS": "k16384f=%d" % v})
-    timing("col 16384 x 4096 c64 four-step", "axis", (1, 16384, 4096), af.C2C, env={"B200FFT_NO_CLUSTER": "1"})
+    timing("col 16384 x 4096 c64 four-step", "axis", (1, 16384, 4096), af.C2C, env={"B200FFT_CLUSTER": "0"})
     timing("col 4096 x 4096 c128 cluster", "axis", (1, 4096, 4096), af.Z2Z)
-    timing("col 4096 x 4096 c128 four-step", "axis", (1, 4096, 4096), af.Z2Z, env={"B200FFT_NO_CLUSTER": "1"})
+    timing("col 4096 x 4096 c128 four-step", "axis", (1, 4096, 4096), af.Z2Z, env={"B200FFT_CLUSTER": "0"})
     timing("col 8192 x 4096 c128 cluster", "axis", (1, 8192, 4096), af.Z2Z)
-    timing("col 8192 x 4096 c128 four-step", "axis", (1, 8192, 4096), af.Z2Z, env={"B200FFT_NO_CLUSTER": "1"})
+    timing("col 8192 x 4096 c128 four-step", "axis", (1, 8192, 4096), af.Z2Z, env={"B200FFT_CLUSTER": "0"})

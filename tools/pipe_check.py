@@ -33,17 +33,17 @@ def parity_1d(n, typ):
     p.destroy()
 
 if "parity" in sys.argv:
-    os.environ["B200FFT_PIPE_MIN_TILES"] = "1"
+    os.environ["B200FFT_PIPE_MIN_TILES"] = "1"; os.environ["B200FFT_PIPE"] = "1"
     for (n, inner, outer) in [(1024, 64, 1), (1024, 512, 3), (2048, 128, 2), (4096, 64, 1), (8192, 64, 1), (8192, 1024, 1), (8192, 256, 2), (16384, 128, 1)]:
         parity_axis(n, inner, af.C2C, outer)
     for (n, inner, outer) in [(512, 64, 1), (512, 256, 3), (1024, 64, 2), (2048, 64, 1), (4096, 128, 1), (8192, 64, 2)]:
         parity_axis(n, inner, af.Z2Z, outer)
     parity_1d(1 << 20, af.C2C)
     parity_1d(1 << 18, af.Z2Z)
-    os.environ.pop("B200FFT_PIPE_MIN_TILES")
+    os.environ.pop("B200FFT_PIPE_MIN_TILES"); os.environ["B200FFT_PIPE"] = "0"
 if "time" in sys.argv:
-    for env in ({}, {"B200FFT_NO_PIPE": "1"}):
-        tag = " nopipe" if env else " pipe"
+    for env in ({"B200FFT_PIPE": "1"}, {"B200FFT_PIPE": "0"}, {"B200FFT_PIPE": "0", "B200FFT_CLUSTER": "0"}):
+        tag = " pipe" if env["B200FFT_PIPE"] == "1" else " nopipe" if len(env) == 1 else " nopipe nocluster"
         timing("col 8192 x 8192 c64" + tag, "axis", (1, 8192, 8192), af.C2C, env=env)
         timing("cfg3 2D 8192^2 c64" + tag, "2d", (8192, 8192), af.C2C, env=env)
         timing("col 1024 x 65536 c64" + tag, "axis", (1, 1024, 65536), af.C2C, env=env)
