@@ -13,7 +13,7 @@ KernelEntry make_pipe_entry() {
   e.S = K::S;
   for (int i = 0; i < 4; i++) e.rad[i] = K::rad[i];
   e.tw_len = K::TW_LEN;
-  e.flavor = FL_PIPE;
+  e.flavor = P::ROWS ? FL_PIPEROW : FL_PIPE;
   e.tw4 = TW4;
   e.threads = P::THREADS;
   e.smem = P::SMEM;
@@ -24,6 +24,7 @@ KernelEntry make_pipe_entry() {
 }
 
 #define REG_PIPE(CS, ...) add(make_pipe_entry<PipeCfg<Cfg<__VA_ARGS__>, CS>, false>())
+#define REG_PIPE_ROWS(...) add(make_pipe_entry<PipeCfg<Cfg<__VA_ARGS__>, 1, 4, true>, false>())
 #define REG_PIPE_TW(CS, ...) add(make_pipe_entry<PipeCfg<Cfg<__VA_ARGS__>, CS>, true>())   // + four-step twiddle at the store
 
 void register_pipe(void (*add)(const KernelEntry&)) {
@@ -34,6 +35,9 @@ void register_pipe(void (*add)(const KernelEntry&)) {
   REG_PIPE(4, float, 1024, 32, 8, 1, 32, 32);
   REG_PIPE(8, float, 1024, 32, 8, 1, 32, 32);            // cfg3's column axis
   REG_PIPE(16, float, 1024, 32, 8, 1, 32, 32);
+  // contiguous rows: one 64 KB line per tile
+  REG_PIPE_ROWS(float, 8192, 32, 1, 1, 32, 16, 16);
+  REG_PIPE_ROWS(double, 4096, 16, 1, 1, 16, 16, 16);
   // c128: 512-point CTA share, 8 columns (128 B runs)
   REG_PIPE(1, double, 512, 16, 8, 1, 16, 16, 2);
   REG_PIPE_TW(1, double, 512, 16, 8, 1, 16, 16, 2);

@@ -67,31 +67,37 @@ __device__ __forceinline__ void st_async(uint32_t addr, double2 v, uint32_t mbar
                : "memory");
 }
 
-template <class K_, int CS_, int NQ_ = 4>
+// ROWS: contiguous lines (one line per tile, row layout in the exchange buffer) instead of strided columns
+template <class K_, int CS_, int NQ_ = 4, bool ROWS_ = false>
 struct PipeCfg {
   using K = K_;
   static constexpr int CS = CS_, G = 2, NQ = NQ_;
+  static constexpr bool ROWS = ROWS_;
+  static_assert(!ROWS_ || (CS_ == 1 && K_::TL == 1), "row mode: one contiguous line per tile, no cluster");
   static constexpr int N1 = K::N, N = K::N * CS_;
   static constexpr int EP = K::E / CS_;          // CS > 1: phase-2 butterflies per thread
   static constexpr int KL = K::N / CS_;          // CS > 1: values of k1 owned by one CTA
   static constexpr int THREADS = G * K::THREADS;
   static constexpr int TILE_ELEMS = K::N * K::TL;
   static constexpr int TILE_BYTES = TILE_ELEMS * K::ESZ;
-  static constexpr int ROW_CHUNKS = K::TL * K::ESZ / 16;                 // 16-byte chunks per row of the tile
+  static constexpr int ROW_CHUNKS = ROWS_ ? TILE_ELEMS * K::ESZ / 16 : K::TL * K::ESZ / 16;   // 16-byte chunks per contiguous run
   static constexpr int PART_CHUNKS = TILE_BYTES / 16 / NQ_;              // chunks per landing part
   static constexpr int CPT = PART_CHUNKS / K::THREADS;                   // cp.async per thread and part
   static constexpr int EQ = K::E / NQ_;                                  // registers fed by one part
-  static constexpr int XCH_ELEMS = (K::COL_ELEMS > TILE_ELEMS) ? K::COL_ELEMS : TILE_ELEMS;
+  static constexpr int LAY_ELEMS = ROWS_ ? K::ROW_ELEMS : K::COL_ELEMS;
+  static constexpr int XCH_ELEMS = (LAY_ELEMS > TILE_ELEMS) ? LAY_ELEMS : TILE_ELEMS;
   static constexpr size_t XCH_BYTES = (((size_t)XCH_ELEMS * K::ESZ + 127) / 128) * 128;
   // the stage twiddles and this rank's row of inner twiddles live in shared memory for the life of the CTA: their
   // global loads queued behind the cp.async stream in the LSU (lg_throttle 22 % of the stall samples)
-  static constexpr int TW_ELEMS = K::TW_LEN + (CS_ > 1 ? K::N : 0);
+  // (when the table fits: the three-stage row kernels keep theirs, 64 KB, in global memory)
+  static constexpr bool TW_SMEM = (size_t)K::TW_LEN * K::ESZ <= 16384;
+  static constexpr int TW_ELEMS = (TW_SMEM ? K::TW_LEN : 0) + (CS_ > 1 ? K::N : 0);
   static constexpr size_t TW_BYTES = (((size_t)TW_ELEMS * K::ESZ + 127) / 128) * 128;
   static constexpr size_t BAR_OFF = (size_t)TILE_BYTES + G * XCH_BYTES + TW_BYTES;
   static constexpr size_t SMEM = BAR_OFF + 8 * (NQ_ + 2 * G) + 16;
   static_assert(K::S >= 2, "needs at least one shared-memory exchange");
   static_assert(K::E % CS_ == 0 && K::E % NQ_ == 0, "E must split over the cluster and over the landing parts");
-  static_assert((K::TL * K::ESZ) % 16 == 0 && PART_CHUNKS % K::THREADS == 0 && K::THREADS % ROW_CHUNKS == 0, "cp.async tiling");
+  static_assert((ROWS_ || (K::TL * K::ESZ) % 16 == 0) && PART_CHUNKS % K::THREADS == 0 && (ROWS_ || K::THREADS % ROW_CHUNKS == 0), "cp.async tiling");
   static_assert(CS_ == 1 || CS_ == 2 || CS_ == 4 || CS_ == 8 || CS_ == 16, "cluster size = register radix of phase 2");
 };
 
@@ -107,6 +113,7 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
   using T = typename K::real;
   using C = cpx_t<T>;
   constexpr int CS = P::CS, NQ = P::NQ, EQ = P::EQ;
+  constexpr bool ROWS = P::ROWS, COL = !P::ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* land = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P::BAR_OFF);
@@ -117,7 +124,7 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
 
   const int grp = threadIdx.x / K::THREADS;
   const int tid = threadIdx.x % K::THREADS;
-  const int l = tid % K::TL, t = tid / K::TL;
+  const int l = ROWS ? 0 : tid % K::TL, t = ROWS ? tid : tid / K::TL;
   const unsigned rank = (CS > 1) ? cluster_ctarank() : 0u;
   const unsigned q0 = (CS > 1) ? cluster_id_x() : blockIdx.x;
   const unsigned nclus = gridDim.x / CS;
@@ -125,10 +132,13 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
   const int nk = (q0 < ntiles) ? (int)((ntiles - q0 + nclus - 1) / nclus) : 0;   // tiles of this CTA: q0 + j*nclus
   C* xch = reinterpret_cast<C*>(smem_raw + P::TILE_BYTES + (size_t)grp * P::XCH_BYTES);
 
-  for (int i = threadIdx.x; i < K::TW_LEN; i += P::THREADS) stw[i] = tws[i];
+  constexpr int TWL = P::TW_SMEM ? K::TW_LEN : 0;   // inner twiddles follow the stage table
+  if constexpr (P::TW_SMEM)
+    for (int i = threadIdx.x; i < K::TW_LEN; i += P::THREADS) stw[i] = tws[i];
+  const C* stage_tw = P::TW_SMEM ? stw : tws;
   if constexpr (CS > 1)
     if (rank != 0)
-      for (int i = threadIdx.x; i < K::N; i += P::THREADS) stw[K::TW_LEN + i] = ctw[(size_t)(rank - 1) * K::N + i];
+      for (int i = threadIdx.x; i < K::N; i += P::THREADS) stw[TWL + i] = ctw[(size_t)(rank - 1) * K::N + i];
   if (threadIdx.x == 0) {
     for (int q = 0; q < NQ; q++) mbar_init(&full[q], K::THREADS);
     for (int i = 0; i < P::G; i++) { mbar_init(&ready[i], CS); mbar_init(&landed[i], 1); }
@@ -154,13 +164,16 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
   auto issue_part = [&](int j, int q) {
     int lt, o, b;
     tile_coords(j, lt, o, b);
-    const char* base = reinterpret_cast<const char*>(in + (long long)b * g.ibs + (long long)o * g.ios + (long long)lt * K::TL +
-                                                     (long long)rank * g.ins);
+    const char* base = reinterpret_cast<const char*>(in + (long long)b * g.ibs + (long long)o * g.ios +
+                                                     (ROWS ? (long long)lt * g.ils : (long long)lt * K::TL + (long long)rank * g.ins));
     static_for<0, P::CPT>([&](auto ic) {
       constexpr int i = ic;
       const int c = q * P::PART_CHUNKS + i * K::THREADS + tid;
-      const int row = c / P::ROW_CHUNKS, sub = c % P::ROW_CHUNKS;
-      cp_async16(land_u32 + (uint32_t)c * 16u, base + (unsigned long long)row * row_b + (unsigned)sub * 16u);
+      if constexpr (ROWS) cp_async16(land_u32 + (uint32_t)c * 16u, base + (unsigned)c * 16u);
+      else {
+        const int row = c / P::ROW_CHUNKS, sub = c % P::ROW_CHUNKS;
+        cp_async16(land_u32 + (uint32_t)c * 16u, base + (unsigned long long)row * row_b + (unsigned)sub * 16u);
+      }
     });
     cp_async_arrive_noinc(&full[q]);
   };
@@ -196,23 +209,23 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
 
     // ---- phase 1: N1-point transform in this group's exchange buffer -----------------------------------
     if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
-    run_stage<K, 0, C, false>(v, t, stw);
-    scatter<K, 0, true>(v, xch, l, t);
+    run_stage<K, 0, C, !P::TW_SMEM>(v, t, stage_tw);
+    scatter<K, 0, COL>(v, xch, l, t);
     static_for<1, K::S - 1>([&](auto sc) {
       constexpr int s = sc;
       group_bar(gbar, K::THREADS);
-      gather<K, true>(v, xch, l, t);
-      run_stage<K, s, C, false>(v, t, stw);
+      gather<K, COL>(v, xch, l, t);
+      run_stage<K, s, C, !P::TW_SMEM>(v, t, stage_tw);
       group_bar(gbar, K::THREADS);
-      scatter<K, s, true>(v, xch, l, t);
+      scatter<K, s, COL>(v, xch, l, t);
     });
     group_bar(gbar, K::THREADS);
-    gather<K, true>(v, xch, l, t);
-    run_stage<K, K::S - 1, C, false>(v, t, stw);    // v[e] = output k1 = t + e*TPT of this CTA's N1-point transform
+    gather<K, COL>(v, xch, l, t);
+    run_stage<K, K::S - 1, C, !P::TW_SMEM>(v, t, stage_tw);    // v[e] = output k1 = t + e*TPT of this CTA's N1-point transform
 
     if constexpr (CS == 1) {
-      const unsigned step_b = (unsigned)((long long)K::TPT * g.ons * (long long)sizeof(C));
-      C* op = out + (long long)b * g.obs + (long long)o * g.oos + line + (long long)t * g.ons;
+      const unsigned step_b = ROWS ? (unsigned)(K::TPT * sizeof(C)) : (unsigned)((long long)K::TPT * g.ons * (long long)sizeof(C));
+      C* op = out + (long long)b * g.obs + (long long)o * g.oos + (ROWS ? (long long)lt * g.ols + t : line + (long long)t * g.ons);
       if constexpr (TW4) {
         const unsigned m = g.tw_from_o ? (unsigned)o : (unsigned)line / (unsigned)g.tw_div;
         const unsigned lomask = (1u << g.tw_lo_bits) - 1u;
@@ -243,7 +256,7 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
       if (tid < CS) mbar_arrive_remote(map_to_rank(smem_u32(&ready[grp]), (unsigned)tid));
       // inner four-step twiddle w_N^(k1 * rank): anchors from ctw[rank-1][k1] + running product (<= 8 ulp)
       if (rank != 0) {
-        const C* wp = stw + K::TW_LEN;
+        const C* wp = stw + TWL;
         constexpr int CH = (K::E < 8) ? K::E : 8;
         const C stepw = wp[K::TPT];
         static_for<0, K::E / CH>([&](auto qc) {

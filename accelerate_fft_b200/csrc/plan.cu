@@ -315,6 +315,7 @@ struct Builder {
       }
     }
     if (flavor == FL_COL) attach_pipe(ps, N, tw4);
+    if (flavor == FL_ROW && !tw4) attach_pipe_rows(ps, N);
     push(ps);
     return true;
   }
@@ -367,6 +368,28 @@ struct Builder {
     snprintf(buf, sizeof buf, " | pipe: N=%dx%d E=%d TL=%d threads=%d smem=%zu tiles=%lld", q->N1, q->CS, q->E, q->TL, q->threads, q->smem, ntiles);
     ps.desc += buf;
   }
+
+  // Persistent pipelined kernel for contiguous rows of one 64 KB line per tile (batched innermost-axis transforms).
+  void attach_pipe_rows(Pass& ps, long long N) {
+    const char* mode = getenv("B200FFT_PIPE");
+    if (mode && atoi(mode) == 0) return;
+    const bool force = mode && atoi(mode) > 0;
+    const KernelEntry* q = find_kernel(p->is_double, (int)N, FL_PIPEROW, 0, 0);
+    if (!q) return;
+    const Geom& g = ps.g;
+    if (g.ils != N || g.ols != N || g.ins != 1 || g.ons != 1 || g.nb != 1 || g.no != 1) return;
+    if (g.nl < env_int("B200FFT_PIPE_MIN_TILES", 2 * 148)) return;
+    if (!force && !pipe_rows_default(N)) return;
+    ps.pipe = q;
+    ps.pipe_ntl = g.nl;
+    ps.ptws = make_stage_twiddles(p, q);
+    ps.pctw = nullptr;
+    ps.ring = nullptr;
+    char buf[200];
+    snprintf(buf, sizeof buf, " | pipe rows: E=%d threads=%d smem=%zu tiles=%d", q->E, q->threads, q->smem, g.nl);
+    ps.desc += buf;
+  }
+  bool pipe_rows_default(long long N) const { (void)N; return false; }
 
   // ---- one launch of a cluster (DSMEM) column kernel: strided axis [O][N][I] in place, N = N1*CS ------
   static int cluster_min_n() { return env_int("B200FFT_CLUSTER_MIN_N", 4096); }

@@ -180,6 +180,127 @@ def test_fft2d_two_pass_row_pair_plan(af, oracle, dtype, mode):
         af.lib().accfft_plan_cache_clear()
 
 
+class _env:
+    """Set planner switches for the duration of a test and drop the cached plans on both sides."""
+
+    def __init__(self, af, **kv):
+        self.af, self.kv, self.old = af, kv, {}
+
+    def __enter__(self):
+        for k, v in self.kv.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = v
+        self.af.lib().accfft_plan_cache_clear()
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        self.af.lib().accfft_plan_cache_clear()
+
+
+def _np_fft2(mode, x):
+    x128 = x.astype(np.complex128)
+    return np.fft.fft2(x128) if mode == "Forward" else np.fft.ifft2(x128) * (1 if mode == "Inverse" else x.size)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_cluster_column_kernel(af, oracle, dtype, mode):
+    """Column axes of 4096..16384 points in ONE pass by a thread-block cluster exchanging through distributed
+    shared memory (cluster_kernel.cuh; opt-in, B200FFT_CLUSTER=1).  Includes a ragged last column tile."""
+    rng = np.random.default_rng(41)
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    shapes = [(4096, 64), (8192, 24), (8192, 100), (16384, 16)] if dtype == np.complex64 else [(4096, 16), (8192, 12), (8192, 37)]
+    with _env(af, B200FFT_CLUSTER="1", B200FFT_PIPE="0"):
+        for shape in shapes:
+            p = af.Plan("2d", list(shape), typ, 1)
+            d = p.describe()
+            p.destroy()
+            assert "cluster cols" in d and len(d.strip().split("\n")) == 2, d
+            x = rand_complex(rng, shape, dtype)
+            y = gpu(af, "fft2D", mode, x)
+            assert rel_l2(y, _np_fft2(mode, x)) <= bar(dtype, x.size), (shape, mode)
+            if shape[0] == 4096:
+                assert rel_l2(y, oracle.fft2D(mode, x, threads=8)) <= bar(dtype, x.size), (shape, mode)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", ["Forward", "Inverse"])
+def test_pipelined_column_kernels(af, oracle, dtype, mode):
+    """The persistent software-pipelined column kernel (pipe_kernel.cuh): cp.async landing FIFO, two thread groups and,
+    for clusters, the st.async + mbarrier exchange.  Forced on for every legal shape (B200FFT_PIPE=1); one tile per
+    CTA up to several tiles per CTA with an odd count; buffers that are not 16-byte aligned take the fallback."""
+    import torch
+    rng = np.random.default_rng(43)
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    n1 = 1024 if dtype == np.complex64 else 512          # the CTA share of the instantiated kernels
+    with _env(af, B200FFT_CLUSTER="1", B200FFT_PIPE="1", B200FFT_PIPE_MIN_TILES="1"):
+        for cs, inner in [(1, 64), (1, 8 * 148 * 3 + 8), (2, 128), (4, 64), (8, 64), (8, 8 * 37), (16, 128)]:
+            shape = (n1 * cs, inner)
+            p = af.Plan("2d", list(shape), typ, 1)
+            d = p.describe()
+            p.destroy()
+            assert "pipe: N=%dx%d" % (n1, cs) in d, d
+            x = rand_complex(rng, shape, dtype)
+            y = gpu(af, "fft2D", mode, x)
+            assert rel_l2(y, _np_fft2(mode, x)) <= bar(dtype, x.size), (shape, mode)
+            if cs in (1, 8) and inner == 64:
+                assert rel_l2(y, oracle.fft2D(mode, x, threads=8)) <= bar(dtype, x.size), (shape, mode)
+        # the four-step first pass (column transform + twiddle at the store) through the pipelined kernel
+        n = n1 * n1
+        x = rand_complex(rng, (2, n), dtype)
+        p = af.Plan("many", [n], typ, 2)
+        assert "col+tw" in p.describe() and "pipe:" in p.describe(), p.describe()
+        p.destroy()
+        y = gpu(af, "fft", mode, x)
+        x128 = x.astype(np.complex128)
+        assert rel_l2(y, np.fft.fft(x128) if mode == "Forward" else np.fft.ifft(x128)) <= bar(dtype, n)
+        # a buffer that is only element-aligned must take the lock-step kernel and still be right
+        shape = (n1 * 8, 64)
+        x = rand_complex(rng, shape, dtype)
+        buf = torch.empty(x.size + 1, dtype=torch.from_numpy(x).dtype, device="cuda")
+        xin = buf[1:].view(shape)
+        xin.copy_(torch.from_numpy(x))
+        if xin.data_ptr() % 16:
+            y = af.fft2D(mode, xin).cpu().numpy()
+            assert rel_l2(y, _np_fft2(mode, x)) <= bar(dtype, x.size)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pipelined_kernels_default_policy_and_rows(af, dtype):
+    """Without any switch the planner takes the pipelined column kernel where it was measured to win (plain / CS=2,
+    tile span <= 256 MB) and nowhere else; the row variant (B200FFT_PIPE=1) agrees with the lock-step row kernel."""
+    import torch
+    rng = np.random.default_rng(47)
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    n1 = 1024 if dtype == np.complex64 else 512
+    p = af.Plan("axis", [16, n1, 512], typ, 1)
+    assert "pipe:" in p.describe(), p.describe()
+    x = rand_complex(rng, (16, n1, 512), dtype)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    p.exec(xd, yd, af.FORWARD)
+    p.destroy()
+    assert rel_l2(yd.cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=1)) <= bar(dtype, n1)
+    for shape in [(1, n1, 1 << 16), (1, n1 * 8, 1024)]:      # span 512 MB / a cluster of 8: not taken by default
+        p = af.Plan("axis", list(shape), typ, 1)
+        assert "pipe:" not in p.describe(), p.describe()
+        p.destroy()
+    n = 8192 if dtype == np.complex64 else 4096
+    x = rand_complex(rng, (2 * 148 + 5, n), dtype)
+    y0 = af.fft("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
+    with _env(af, B200FFT_PIPE="1"):
+        p = af.Plan("many", [n], typ, x.shape[0])
+        assert "pipe rows" in p.describe(), p.describe()
+        p.destroy()
+        y1 = af.fft("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
+    assert rel_l2(y1, np.fft.fft(x.astype(np.complex128), axis=1)) <= bar(dtype, n)
+    assert rel_l2(y1, y0) <= bar(dtype, n) / 10
+
+
 SHAPES_3D = [(1, 1, 1), (2, 2, 2), (16, 32, 64), (64, 32, 16), (10, 12, 14), (3, 5, 7), (5, 64, 33), (4, 1024, 8), (1024, 4, 8),
              (64, 64, 64), (16, 16, 4096)]
 
