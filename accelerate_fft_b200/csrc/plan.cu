@@ -76,16 +76,21 @@ static int forced_variant(int is_double, int N, int flavor) {
   return 0;
 }
 
-const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int prefer_tl) {
+// max_tl > 0: the number of lines available to a tile -- among the variants, the first (registration order) whose
+// tile is not wider than that, else the narrowest; a forced variant (B200FFT_VARIANTS) always wins.
+const KernelEntry* find_kernel(int is_double, int N, int flavor, int tw4, int max_tl) {
   ensure_registry();
-  (void)prefer_tl;
   const int want = forced_variant(is_double, N, flavor);
-  const KernelEntry* first = nullptr;
+  const bool forced = getenv("B200FFT_VARIANTS") && want > 0;
+  const KernelEntry *first = nullptr, *fit = nullptr, *narrow = nullptr;
   for (const auto& e : reg()) {
     if (e.is_double != is_double || e.N != N || e.flavor != flavor || e.tw4 != tw4) continue;
     if (!first) first = &e;
-    if (e.variant == want) return &e;
+    if (forced && e.variant == want) return &e;
+    if (!fit && max_tl > 0 && e.TL <= max_tl) fit = &e;
+    if (!narrow || e.TL < narrow->TL) narrow = &e;
   }
+  if (max_tl > 0 && first && first->TL > max_tl) return fit ? fit : narrow;
   return first;
 }
 const FusedEntry* find_fused(int is_double, int NA, int flavA, int twA, int NB, int flavB) {
@@ -277,7 +282,8 @@ struct Builder {
   // ---- one launch of a pow2 line kernel --------------------------------------------------
   // array viewed as [nb][no][N-axis...]; see Geom.  Returns false if no kernel exists.
   bool lines_pass(int N, int flavor, bool tw4, Geom g, long long twL, bool inplace_ok, int prefer_tl, const char* what) {
-    const KernelEntry* k = find_kernel(p->is_double, N, flavor, tw4 ? 1 : 0, prefer_tl);
+    (void)prefer_tl;
+    const KernelEntry* k = find_kernel(p->is_double, N, flavor, tw4 ? 1 : 0, (flavor == FL_COL || flavor == FL_TRANS) ? g.nl : 0);
     if (!k) return false;
     Pass ps;
     ps.kind = PK_LINES;
