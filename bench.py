@@ -100,7 +100,11 @@ class ClockSampler:
 
 
 def dominant_kernel(plan_desc):
-    return "fft_ring_rows_kernel" if any("| ring:" in d for d in plan_desc) else "fft_lines_kernel"
+    if any("| ring:" in d for d in plan_desc):
+        return "fft_ring_rows_kernel"
+    if any("| pipe" in d for d in plan_desc):
+        return "fft_lines_kernel + fft_pipe_cols_kernel"
+    return "fft_lines_kernel"
 
 
 def flops_of(cfg, batch):
@@ -330,6 +334,26 @@ def main_gpu(args):
                 "algorithmic_bytes_per_exec": alg_bytes, "exec_ms": exec_ms, "exec_samples": len(samples),
                 "how": "CUDA events around every transform inside the timed region, mean over %d transforms" % len(samples),
                 "per_pass_frac": (npass * 2 * nbytes) / (exec_ms * 1e-3) / 1e9 / peak, "plan": plan_desc}
+
+    # a device copy of the SAME size through the same rotation: what "HBM speed" means for this working set
+    # (a 32 MB copy reaches ~71 % of the large-copy peak: ramp-up and drain of a ~15 us kernel)
+    try:
+        ys = [torch.empty_like(x) for x in xs]
+        for i in range(3):
+            ys[i % nbuf].copy_(xs[i % nbuf])
+        torch.cuda.synchronize()
+        ev0.record()
+        ncopy = max(5, args.steps)
+        for i in range(ncopy):
+            ys[i % nbuf].copy_(xs[i % nbuf])
+        ev1.record()
+        torch.cuda.synchronize()
+        copy_ms = ev0.elapsed_time(ev1) / ncopy
+        del ys
+        roofline["same_size_copy_gbs"] = 2 * nbytes / (copy_ms * 1e-3) / 1e9
+        roofline["frac_of_same_size_copy"] = achieved / roofline["same_size_copy_gbs"]
+    except Exception:
+        pass
 
     # ---- end to end through host buffers (pinned H2D of the input, D2H of the result) ----------
     e2e = None
