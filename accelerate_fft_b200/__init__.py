@@ -188,6 +188,18 @@ class Plan:
             st = lib().b200fftExecScaled(self.h, src.data_ptr(), dst.data_ptr(), direction, float(scale), ctypes.c_void_p(stream))
         _lib.check(st, "exec")
 
+    def exec_scatter(self, src, out_ptrs, out_outer_stride, out_n_stride, direction, stream=None, scale=1.0):
+        """b200fftExecScatter: the pass's stores go to the buffers `out_ptrs` (raw device addresses, possibly of
+        peer GPUs), split by output index."""
+        torch = _torch()
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        arr = (ctypes.c_void_p * len(out_ptrs))(*out_ptrs)
+        src_ptr = src.data_ptr() if hasattr(src, "data_ptr") else int(src)
+        st = lib().b200fftExecScatter(self.h, src_ptr, arr, len(out_ptrs), out_outer_stride, out_n_stride, direction,
+                                      float(scale), ctypes.c_void_p(stream))
+        _lib.check(st, "exec_scatter")
+
     @property
     def num_passes(self):
         return lib().b200fftNumPasses(self.h)

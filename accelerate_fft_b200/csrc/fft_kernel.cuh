@@ -25,7 +25,18 @@ struct Geom {
   // PRE2 ("row pair") kernels only: the tile's input is x[n] + (-1)^line * x[n + pre2_off] -- the radix-2 first
   // stage of a strided axis of length 2*M folded into the row pass; the result is multiplied by w_{2M}^(line*o)
   long long pre2_off;
+  // Scatter store over peer memory (column kernels only; b200fftExecScatter): output index n of the transformed axis
+  // lands in buffer peer[n >> peer_shift] at index n & (2^peer_shift - 1) -- the all-to-all of the slab-decomposed
+  // 3D transform folded into the pass's own stores (NVLink peer addresses are ordinary global addresses).
+  int npeers, peer_shift;
+  void* peer[16];
 };
+
+// address of output index k of (b, o, line) under the scatter store
+template <typename C>
+__device__ __forceinline__ C* peer_addr(const Geom& g, long long off, int k) {
+  return reinterpret_cast<C*>(g.peer[k >> g.peer_shift]) + off + (long long)(k & ((1 << g.peer_shift) - 1)) * g.ons;
+}
 
 template <typename T_, int N_, int E_, int TL_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1>
 struct Cfg {
@@ -262,6 +273,15 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
         static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
       } else if constexpr (CJ) {
         static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
+      }
+      if constexpr (LLF && SLF && !TW4 && !CG) {
+        if (g.npeers) {   // CTA-uniform
+          if (valid) {
+            const long long off = (long long)b * g.obs + (long long)o * g.oos + (long long)line * g.ols;
+            static_for<0, K::E>([&](auto ec) { constexpr int e = ec; *peer_addr<C>(g, off, t + e * K::TPT) = v[e]; });
+          }
+          return;
+        }
       }
       if (valid) {
         char* p = reinterpret_cast<char*>(op);

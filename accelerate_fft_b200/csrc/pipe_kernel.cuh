@@ -244,11 +244,16 @@ fft_pipe_cols_kernel(const Geom g, const cpx_t<typename P::K::real>* __restrict_
       }
       const T sy = g.swap_out ? -scale : scale;
       if (scale != (T)1 || g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
-      char* p = reinterpret_cast<char*>(op);
-      static_for<0, K::E>([&](auto ec) {
-        constexpr int e = ec;
-        st_stream(reinterpret_cast<C*>(p + (unsigned long long)(unsigned)e * step_b), v[e]);
-      });
+      if (!ROWS && !TW4 && g.npeers) {   // scatter store over peer memory (see Geom)
+        const long long off = (long long)b * g.obs + (long long)o * g.oos + line;
+        static_for<0, K::E>([&](auto ec) { constexpr int e = ec; *peer_addr<C>(g, off, t + e * K::TPT) = v[e]; });
+      } else {
+        char* p = reinterpret_cast<char*>(op);
+        static_for<0, K::E>([&](auto ec) {
+          constexpr int e = ec;
+          st_stream(reinterpret_cast<C*>(p + (unsigned long long)(unsigned)e * step_b), v[e]);
+        });
+      }
     } else {
       constexpr int EP = P::EP, KL = P::KL;
       // this group has drained its exchange buffer: tell every CTA of the cluster (lanes 0..CS-1 of the first warp)

@@ -1116,6 +1116,79 @@ int b200fftExec(b200fftHandle plan, const void* in, void* out, int direction, b2
   return b200fftExecScaled(plan, in, out, direction, 1.0, stream);
 }
 
+// One strided-axis pass whose stores are scattered over peer buffers: output index n of the transformed axis goes
+// to outs[n / (N/npeers)] at local index n % (N/npeers); within a buffer the element of (outer o, index nl, inner i)
+// sits at o*out_outer_stride + nl*out_n_stride + i.  See include/b200fft.h.
+int b200fftExecScatter(b200fftHandle p, const void* in, void* const* outs, int npeers, int64_t out_outer_stride,
+                       int64_t out_n_stride, int direction, double scale, b200fftStream stream_) {
+  if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
+  if (!in || !outs || npeers < 1 || npeers > 16) return B200FFT_INVALID_VALUE;
+  if (direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) return B200FFT_INVALID_VALUE;
+  if (p->passes.size() != 1) return B200FFT_NOT_SUPPORTED;
+  const Pass& ps = p->passes[0];
+  if (ps.kind != PK_LINES || ps.k->flavor != FL_COL || ps.k->tw4) return B200FFT_NOT_SUPPORTED;
+  const long long N = ps.k->N;
+  if (N % npeers || !is_pow2(N / npeers)) return B200FFT_INVALID_SIZE;
+  for (int i = 0; i < npeers; i++)
+    if (!outs[i] || outs[i] == in) return B200FFT_INVALID_VALUE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int inverse = direction == B200FFT_INVERSE;
+  Geom g = ps.g;
+  g.swap_in = inverse;
+  g.swap_out = inverse;
+  g.obs = 0; g.oos = out_outer_stride; g.ons = out_n_stride;
+  g.npeers = npeers;
+  g.peer_shift = ilog2(N / npeers);
+  for (int i = 0; i < npeers; i++) g.peer[i] = outs[i];
+  float scf = (float)scale;
+  double scd = scale;
+  void* dst = outs[0];
+  cudaError_t ce;
+  if (ps.pipe && ps.pipe->CS == 1 && ((uintptr_t)in & 15) == 0) {
+    g.ntl = ps.pipe_ntl;
+    void* args[] = {&g, (void*)&in, (void*)&dst, (void*)&ps.ptws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                    p->is_double ? (void*)&scd : (void*)&scf, (void*)&ps.pctw};
+    ce = cudaLaunchKernel(ps.pipe->func, dim3((unsigned)ps.pipe_grid), dim3(ps.pipe->threads), args, ps.pipe->smem, stream);
+  } else {
+    void* args[] = {&g, (void*)&in, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                    p->is_double ? (void*)&scd : (void*)&scf};
+    ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (ce != cudaSuccess) { cudaGetLastError(); return B200FFT_EXEC_FAILED; }
+  return B200FFT_SUCCESS;
+}
+
+// Device buffers that other processes of the box can map (CUDA IPC): the peer buffers of b200fftExecScatter.
+int b200fftPeerAlloc(void** ptr, size_t bytes) {
+  if (!ptr || !bytes) return B200FFT_INVALID_VALUE;
+  if (cudaMalloc(ptr, bytes) != cudaSuccess) { cudaGetLastError(); return B200FFT_ALLOC_FAILED; }
+  return B200FFT_SUCCESS;
+}
+int b200fftPeerFree(void* ptr) {
+  if (cudaFree(ptr) != cudaSuccess) { cudaGetLastError(); return B200FFT_INVALID_VALUE; }
+  return B200FFT_SUCCESS;
+}
+int b200fftPeerExport(void* ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (!ptr || !handle) return B200FFT_INVALID_VALUE;
+  if (cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) { cudaGetLastError(); return B200FFT_NOT_SUPPORTED; }
+  memcpy(handle, &h, 64);
+  return B200FFT_SUCCESS;
+}
+int b200fftPeerOpen(const unsigned char handle[64], void** ptr) {
+  cudaIpcMemHandle_t h;
+  if (!ptr || !handle) return B200FFT_INVALID_VALUE;
+  memcpy(&h, handle, 64);
+  if (cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return B200FFT_NOT_SUPPORTED; }
+  return B200FFT_SUCCESS;
+}
+int b200fftPeerClose(void* ptr) {
+  if (cudaIpcCloseMemHandle(ptr) != cudaSuccess) { cudaGetLastError(); return B200FFT_INVALID_VALUE; }
+  return B200FFT_SUCCESS;
+}
+
 int b200fftDestroy(b200fftHandle p) {
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
   p->magic = 0;

@@ -92,6 +92,22 @@ int b200fftDescribe(b200fftHandle plan, char* buf, int buflen);
 int b200fftSlabPack(int type, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks, b200fftStream stream);
 int b200fftSlabUnpack(int type, const void* src, void* dst, int64_t dl, int64_t h, int64_t w, int nranks, b200fftStream stream);
 
+/* The exchange folded into the pass: one strided-axis plan (b200fftPlanAxis with n a power of two <= 2048) whose
+ * stores are scattered over `npeers` buffers -- output index k of the transformed axis goes to outs[k / (n/npeers)]
+ * at local index k % (n/npeers); inside a buffer the element of (outer o, local index kl, inner i) sits at
+ * o*out_outer_stride + kl*out_n_stride + i (strides in complex elements).  The buffers may live on other GPUs of
+ * the box (peer-mapped over NVLink): the y-axis pass of the slab-decomposed fft3D writes every ky row straight into
+ * the memory of the rank that owns it, so pack + all-to-all + unpack disappear.  The caller orders the exchange
+ * (a barrier on all ranks before the buffers are overwritten and after the kernel has finished). */
+int b200fftExecScatter(b200fftHandle plan, const void* in, void* const* outs, int npeers, int64_t out_outer_stride,
+                       int64_t out_n_stride, int direction, double scale, b200fftStream stream);
+/* Device buffers another process of the same box can map (CUDA IPC, 64-byte handles exchanged by the caller). */
+int b200fftPeerAlloc(void** ptr, size_t bytes);
+int b200fftPeerFree(void* ptr);
+int b200fftPeerExport(void* ptr, unsigned char handle[64]);
+int b200fftPeerOpen(const unsigned char handle[64], void** ptr);
+int b200fftPeerClose(void* ptr);
+
 /*
  * Host-side mirror of the reference's public API for this path (FFT.hs:63-173 + PTX.hs +
  * PTX/Plans.hs): shape/rank dispatch, Mode semantics, the five plan caches and the Inverse
