@@ -1144,7 +1144,9 @@ int b200fftExecScatter(b200fftHandle p, const void* in, void* const* outs, int n
   double scd = scale;
   void* dst = outs[0];
   cudaError_t ce;
-  if (ps.pipe && ps.pipe->CS == 1 && ((uintptr_t)in & 15) == 0) {
+  // NVLink wants long runs: the lock-step kernel stores 128 B per row (TL = 16), the pipelined one 64 B -- measured on
+  // 2 x B200, 1024^3: 6.24 ms against 8.30 ms per transform -- so the pipelined kernel only serves a single target
+  if (npeers == 1 && ps.pipe && ps.pipe->CS == 1 && ((uintptr_t)in & 15) == 0) {
     g.ntl = ps.pipe_ntl;
     void* args[] = {&g, (void*)&in, (void*)&dst, (void*)&ps.ptws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
                     p->is_double ? (void*)&scd : (void*)&scf, (void*)&ps.pctw};
