@@ -203,7 +203,7 @@ class PeerSlabFFT3D:
     there is no pack kernel, no NCCL all-to-all and no unpack; natural-layout output does the same on the way back
     in the z-axis pass.  Ranks only meet in two tiny barriers per transform."""
 
-    def __init__(self, d, h, w, dtype, group=None):
+    def __init__(self, d, h, w, dtype, group=None, chunks=1):
         import torch
         import torch.distributed as dist
         from . import Plan, C2C, Z2Z
@@ -212,8 +212,13 @@ class PeerSlabFFT3D:
         self.geom = g = SlabGeometry(d, h, w, self.world)
         typ = C2C if dtype == torch.complex64 else Z2Z
         self.dtype = dtype
-        self.px = Plan("axis", (g.dl * h, w, 1), typ)
-        self.py = Plan("axis", (g.dl, h, w), typ)
+        # the slab's planes can go through x then y in `chunks` pieces on two streams (x pass of piece c+1 under the
+        # scattered y pass of piece c).  Measured on 2 x B200: no gain (6.25 vs 6.24 ms) -- the y kernel holds every
+        # register of the SMs it runs on, so the x kernels queue behind it instead of sharing the SMs; default 1.
+        self.bounds = g.chunk_bounds(chunks)
+        dlc = self.bounds[0][1] - self.bounds[0][0]
+        self.px = Plan("axis", (dlc * h, w, 1), typ)
+        self.py = Plan("axis", (dlc, h, w), typ)
         self.pz = Plan("axis", (1, d, g.hl * w), typ)
         esz = 8 if dtype == torch.complex64 else 16
         self.esz = esz
@@ -225,21 +230,36 @@ class PeerSlabFFT3D:
         self.ty, self.tz = ty, tz
         self.y_ptrs = [p + ty["offset"] * esz for p in self.recv.ptrs]
         self.z_ptrs = [p + tz["offset"] * esz for p in self.back.ptrs]
+        self.side = torch.cuda.Stream()
+        self.ev_x = [torch.cuda.Event() for _ in self.bounds]
+        self.ev_start, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
 
     def _barrier(self):
         self.dist.all_reduce(self.flag, group=self.group)     # stream-ordered: every rank's kernels so far are done
 
     def __call__(self, mode, x_local, transposed_out=False):
         from . import FORWARD, INVERSE, Inverse, Forward
-        g = self.geom
+        g, torch = self.geom, self.torch
         sign = FORWARD if mode == Forward else INVERSE
         scale = 1.0 / float(g.d * g.h * g.w) if mode == Inverse else 1.0
-        self.px.exec(x_local, self.tmp, sign)
+        main = torch.cuda.current_stream()
+        # x passes on the side stream, piece by piece
+        self.ev_start.record(main)
+        self.side.wait_event(self.ev_start)
+        with torch.cuda.stream(self.side):
+            for c, (z0, z1) in enumerate(self.bounds):
+                self.px.exec(x_local[z0:z1], self.tmp[z0:z1], sign)
+                self.ev_x[c].record(self.side)
+        x_local.record_stream(self.side)
         self._barrier()                                        # peers have consumed `recv` / `back` of the previous call
-        self.py.exec_scatter(self.tmp, self.y_ptrs, self.ty["outer_stride"], self.ty["n_stride"], sign)
+        plane = g.hl * g.w * self.esz
+        for c, (z0, z1) in enumerate(self.bounds):
+            main.wait_event(self.ev_x[c])
+            self.py.exec_scatter(self.tmp[z0:z1], [p + z0 * plane for p in self.y_ptrs], self.ty["outer_stride"],
+                                 self.ty["n_stride"], sign)
         self._barrier()                                        # every ky row has landed
         if transposed_out:
-            out = self.torch.empty((g.d, g.hl, g.w), dtype=self.dtype, device="cuda")
+            out = torch.empty((g.d, g.hl, g.w), dtype=self.dtype, device="cuda")
             self.pz.exec(self.recv.tensor, out, sign, scale=scale)
             return out
         self.pz.exec_scatter(self.recv.tensor, self.z_ptrs, self.tz["outer_stride"], self.tz["n_stride"], sign, scale=scale)
