@@ -120,3 +120,42 @@ def test_slab_geometry_validation():
     assert g.chunk_bounds(3) == [(0, 64), (64, 128)]     # falls back to a divisor
     with pytest.raises(ValueError):
         SlabGeometry(10, 8, 8, 4)
+
+
+def _emulate_exec_scatter(y, outs, offset, outer_stride, n_stride):
+    """The index contract of b200fftExecScatter (include/b200fft.h) in numpy: `y` is the transformed [outer][n][inner]
+    array; output index k of the axis goes to outs[k // (n/npeers)] (flat buffers) at
+    offset + o*outer_stride + (k % (n/npeers))*n_stride + i."""
+    outer, n, inner = y.shape
+    nl = n // len(outs)
+    for o in range(outer):
+        for k in range(n):
+            base = offset + o * outer_stride + (k % nl) * n_stride
+            outs[k // nl][base:base + inner] = y[o, k]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_scatter_index_arithmetic(world):
+    """slab.scatter_targets + the ExecScatter contract reproduce fft3D: every rank's y pass scatters its ky rows
+    into the owners' [D][hl][W] buffers, the z pass scatters back into z-slabs (PeerSlabFFT3D without the GPUs)."""
+    from accelerate_fft_b200.slab import SlabGeometry, scatter_targets
+    d, h, w = 8, 12, 5
+    rng = np.random.default_rng(3)
+    full = rng.uniform(-1, 1, (d, h, w)) + 1j * rng.uniform(-1, 1, (d, h, w))
+    ref = np.fft.fftn(full)
+    g = SlabGeometry(d, h, w, world)
+    recv = [np.zeros(d * g.hl * w, dtype=np.complex128) for _ in range(world)]
+    back = [np.zeros(g.dl * h * w, dtype=np.complex128) for _ in range(world)]
+    for r in range(world):
+        mine = full[r * g.dl:(r + 1) * g.dl]
+        a = np.fft.fft(np.fft.fft(mine, axis=2), axis=1)                  # x then y on the slab: [dl][H][W]
+        ty, _ = scatter_targets(g, r)
+        _emulate_exec_scatter(a, recv, ty["offset"], ty["outer_stride"], ty["n_stride"])
+    for r in range(world):
+        b = recv[r].reshape(d, g.hl, w)
+        assert np.allclose(np.fft.fft(b, axis=0), ref[:, r * g.hl:(r + 1) * g.hl], atol=1e-9)     # transposed-out result
+        c = np.fft.fft(b, axis=0).reshape(1, d, g.hl * w)                 # z pass viewed as [1][D][hl*W]
+        _, tz = scatter_targets(g, r)
+        _emulate_exec_scatter(c, back, tz["offset"], tz["outer_stride"], tz["n_stride"])
+    for r in range(world):
+        assert np.allclose(back[r].reshape(g.dl, h, w), ref[r * g.dl:(r + 1) * g.dl], atol=1e-9)
