@@ -102,6 +102,83 @@ def fft3D(mode, arr):
     return out
 
 
+# ---- Data.Array.Accelerate.Math.DFT.Centre (DFT/Centre.hs): the step on either side of the transform ------------
+
+def _centre_like(arr, rank, call, what):
+    if arr.dim() != rank:
+        raise ValueError("%s needs a DIM%d array" % (what, rank))
+    arr, out, typ, stream = _prep(arr)
+    torch = _torch()
+    with torch.cuda.device(arr.device):
+        _lib.check(call(arr, out, typ, stream), what)
+    return out
+
+
+def _centre(arr, rank):
+    return _centre_like(arr, rank, lambda a, o, t, s: lib().accfft_centre(rank, _shape(a), t, a.data_ptr(), o.data_ptr(), s),
+                        "centre%dD" % rank)
+
+
+def _shift(arr, rank, inverse):
+    return _centre_like(arr, rank, lambda a, o, t, s: lib().accfft_shift(rank, _shape(a), t, inverse, a.data_ptr(), o.data_ptr(), s),
+                        ("ishift%dD" if inverse else "shift%dD") % rank)
+
+
+def centre1D(arr):
+    """(-1)^x * arr (Centre.hs:36-43)."""
+    return _centre(arr, 1)
+
+
+def centre2D(arr):
+    """(-1)^(y+x) * arr (Centre.hs:47-54)."""
+    return _centre(arr, 2)
+
+
+def centre3D(arr):
+    """(-1)^(z+y+x) * arr (Centre.hs:58-65)."""
+    return _centre(arr, 3)
+
+
+def shift1D(arr):
+    """out[i] = arr[(i + n/2 + odd n) rem n] (Centre.hs:70-79)."""
+    return _shift(arr, 1, 0)
+
+
+def shift2D(arr):
+    return _shift(arr, 2, 0)     # Centre.hs:98-112
+
+
+def shift3D(arr):
+    return _shift(arr, 3, 0)     # Centre.hs:134-151
+
+
+def ishift1D(arr):
+    """out[i] = arr[(i + n/2) rem n] (Centre.hs:84-94)."""
+    return _shift(arr, 1, 1)
+
+
+def ishift2D(arr):
+    return _shift(arr, 2, 1)     # Centre.hs:116-130
+
+
+def ishift3D(arr):
+    return _shift(arr, 3, 1)     # Centre.hs:155-164
+
+
+def fft_centred(mode, arr):
+    """shiftND (fftND mode arr) for a DIM1/2/3 array in one call -- zero frequency in the middle; for even extents this is
+    fftND mode (centreND arr) (Centre.hs:17-19).  Power-of-two extents: the rotation rides on the stores of each axis' last
+    butterfly pass (b200fftExecShifted), no extra pass over the array."""
+    if arr.dim() not in (1, 2, 3):
+        raise ValueError("fft_centred needs a DIM1, DIM2 or DIM3 array")
+    arr, out, typ, stream = _prep(arr)
+    torch = _torch()
+    with torch.cuda.device(arr.device):
+        _lib.check(lib().accfft_fft_centred(arr.dim(), _MODE[mode], _shape(arr), typ, arr.data_ptr(), out.data_ptr(), stream),
+                   "fft_centred")
+    return out
+
+
 def run_host(kind, mode, a):
     """Host-buffer entry (numpy in, numpy out): H2D copy + transform + D2H copy through the C ABI.
     kind in {"fft","fft1D","fft2D","fft3D"}."""

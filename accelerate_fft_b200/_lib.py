@@ -21,6 +21,7 @@ EXPORTS = [
     "accfft_fft", "accfft_fft1D", "accfft_fft2D", "accfft_fft3D", "accfft_run_host", "accfft_run_host_seq",
     "accfft_set_fused_inverse", "accfft_plan_cache_size", "accfft_plan_cache_clear",
     "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack", "b200fftTrimScratch",
+    "b200fftExecShifted", "accfft_centre", "accfft_shift", "accfft_fft_centred",
     "b200fftExecScatter", "b200fftPeerAlloc", "b200fftPeerFree", "b200fftPeerExport", "b200fftPeerOpen", "b200fftPeerClose",
 ]
 
@@ -85,6 +86,10 @@ def lib():
     L.b200fftPlanAxis.argtypes = [pvp, i64, i64, i64, i]
     L.b200fftSlabPack.argtypes = [i, vp, vp, i64, i64, i64, i, vp]
     L.b200fftSlabUnpack.argtypes = [i, vp, vp, i64, i64, i64, i, vp]
+    L.b200fftExecShifted.argtypes = [vp, vp, vp, i, d, vp]
+    L.accfft_centre.argtypes = [i, pi64, i, vp, vp, vp]
+    L.accfft_shift.argtypes = [i, pi64, i, i, vp, vp, vp]
+    L.accfft_fft_centred.argtypes = [i, i, pi64, i, vp, vp, vp]
     L.b200fftExecScatter.argtypes = [vp, vp, pvp, i, i64, i64, i, d, vp]
     L.b200fftPeerAlloc.argtypes = [pvp, ctypes.c_size_t]
     L.b200fftPeerFree.argtypes = [vp]

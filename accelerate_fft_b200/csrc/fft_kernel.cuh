@@ -9,6 +9,9 @@
 #include "cplx.cuh"
 
 namespace b200fft {
+#ifndef ROWROT_ENABLED
+#define ROWROT_ENABLED true
+#endif
 
 // Where the lines of one launch live.  All strides in complex elements.
 //   address(b, o, line, n) = b*bs + o*os + line*ls + n*ns
@@ -25,9 +28,11 @@ struct Geom {
   // PRE2 ("row pair") kernels only: the tile's input is x[n] + (-1)^line * x[n + pre2_off] -- the radix-2 first
   // stage of a strided axis of length 2*M folded into the row pass; the result is multiplied by w_{2M}^(line*o)
   long long pre2_off;
-  // Scatter store over peer memory (column kernels only; b200fftExecScatter): output index n of the transformed axis
-  // lands in buffer peer[n >> peer_shift] at index n & (2^peer_shift - 1) -- the all-to-all of the slab-decomposed
-  // 3D transform folded into the pass's own stores (NVLink peer addresses are ordinary global addresses).
+  // Scatter store: output index n of the transformed axis lands in buffer peer[n >> peer_shift] at index
+  // n & (2^peer_shift - 1).  With the buffers of other GPUs (b200fftExecScatter) it is the all-to-all of the
+  // slab-decomposed 3D transform folded into the pass's own stores (NVLink peer addresses are ordinary global
+  // addresses); with peer[0] = out + N/2 and peer[1] = out it is the half rotation of DFT/Centre.hs's `shift`
+  // (b200fftExecShifted) -- both free in the last butterfly pass.
   int npeers, peer_shift;
   void* peer[16];
 };
@@ -274,12 +279,20 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
       } else if constexpr (CJ) {
         static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
       }
-      if constexpr (LLF && SLF && !TW4 && !CG) {
-        if (g.npeers) {   // CTA-uniform
+      if constexpr (SLF && !TW4 && !CG) {
+        if (g.npeers) {   // CTA-uniform: scatter store (see Geom)
           if (valid) {
             const long long off = (long long)b * g.obs + (long long)o * g.oos + (long long)line * g.ols;
             static_for<0, K::E>([&](auto ec) { constexpr int e = ec; *peer_addr<C>(g, off, t + e * K::TPT) = v[e]; });
           }
+          return;
+        }
+      }
+      if constexpr (!SLF && !TW4 && !CG && !PRE2 && K::E >= 2 && ROWROT_ENABLED) {
+        // contiguous lines: the half rotation of b200fftExecShifted is a rotation of the register index -- output
+        // t + e*TPT lands at t + ((e + E/2) mod E)*TPT, compile-time offsets, no address arithmetic
+        if (g.npeers) {
+          if (valid) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; op[((e + K::E / 2) % K::E) * K::TPT] = v[e]; });
           return;
         }
       }

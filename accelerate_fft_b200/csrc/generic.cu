@@ -382,6 +382,43 @@ cudaError_t launch_slab_pack(int is_double, bool pack, const void* src, void* ds
   return cudaGetLastError();
 }
 
+// DFT/Centre.hs:70-164 shift*/ishift*: backpermute, dst[z][y][x] = src[(z+sd)%d][(y+sh)%h][(x+sw)%w]
+template <typename C>
+__global__ void shift_kernel(const C* __restrict__ src, C* __restrict__ dst, long long d, long long h, long long w, long long sd,
+                             long long sh, long long sw) {
+  const long long total = d * h * w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long x = idx % w, y = (idx / w) % h, z = idx / (w * h);
+    dst[idx] = src[(((z + sd) % d) * h + (y + sh) % h) * w + (x + sw) % w];
+  }
+}
+// DFT/Centre.hs:36-66 centre*: dst = (-1)^(z+y+x) * src
+template <typename C>
+__global__ void centre_kernel(const C* __restrict__ src, C* __restrict__ dst, long long d, long long h, long long w) {
+  const long long total = d * h * w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long x = idx % w, y = (idx / w) % h, z = idx / (w * h);
+    C v = src[idx];
+    if ((x + y + z) & 1) { v.x = -v.x; v.y = -v.y; }
+    dst[idx] = v;
+  }
+}
+static unsigned ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+cudaError_t launch_shift(int is_double, const void* src, void* dst, long long d, long long h, long long w, long long sd, long long sh,
+                         long long sw, cudaStream_t stream) {
+  if (is_double) shift_kernel<double2><<<ew_blocks(d * h * w), 256, 0, stream>>>((const double2*)src, (double2*)dst, d, h, w, sd, sh, sw);
+  else shift_kernel<float2><<<ew_blocks(d * h * w), 256, 0, stream>>>((const float2*)src, (float2*)dst, d, h, w, sd, sh, sw);
+  return cudaGetLastError();
+}
+cudaError_t launch_centre(int is_double, const void* src, void* dst, long long d, long long h, long long w, cudaStream_t stream) {
+  if (is_double) centre_kernel<double2><<<ew_blocks(d * h * w), 256, 0, stream>>>((const double2*)src, (double2*)dst, d, h, w);
+  else centre_kernel<float2><<<ew_blocks(d * h * w), 256, 0, stream>>>((const float2*)src, (float2*)dst, d, h, w);
+  return cudaGetLastError();
+}
+
 int generic_set_attrs() {
   if (cudaFuncSetAttribute(mixed_radix_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;

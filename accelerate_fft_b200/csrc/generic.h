@@ -42,6 +42,10 @@ cudaError_t launch_copy_scale(int is_double, const void* src, void* dst, long lo
                               long long* nlaunches);
 cudaError_t launch_slab_pack(int is_double, bool pack, const void* src, void* dst, long long dl, long long h, long long w, int P,
                              cudaStream_t stream);
+// DFT/Centre.hs as stand-alone elementwise passes (rank <= 3 viewed as [d][h][w])
+cudaError_t launch_shift(int is_double, const void* src, void* dst, long long d, long long h, long long w, long long sd, long long sh,
+                         long long sw, cudaStream_t stream);
+cudaError_t launch_centre(int is_double, const void* src, void* dst, long long d, long long h, long long w, cudaStream_t stream);
 int generic_set_attrs();
 // stream-ordered allocation from the library-owned scratch pool (plan.cu); release with cudaFreeAsync
 cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t stream);

@@ -152,6 +152,60 @@ int accfft_fft3D(int mode, int64_t d, int64_t h, int64_t w, int type, const void
   return run(fft3D_plans, mode, d, h, w, type, (double)d * (double)h * (double)w, in, out, stream);  // FFT.hs:155
 }
 
+// ---- DFT/Centre.hs: the step on either side of the path in image / signal pipelines ----------
+static int dims3(int rank, const int64_t* shape, long long* d, long long* h, long long* w) {
+  if (rank < 1 || rank > 3 || !shape) return B200FFT_INVALID_VALUE;
+  for (int i = 0; i < rank; i++) if (shape[i] < 0) return B200FFT_INVALID_SIZE;
+  *w = shape[rank - 1];
+  *h = rank >= 2 ? shape[rank - 2] : 1;
+  *d = rank >= 3 ? shape[rank - 3] : 1;
+  return 0;
+}
+// centre1D/2D/3D (Centre.hs:36-66): out = (-1)^(sum of indices) * in
+int accfft_centre(int rank, const int64_t* shape, int type, const void* in, void* out, b200fftStream stream) {
+  long long d, h, w;
+  if (int e = dims3(rank, shape, &d, &h, &w)) return e;
+  if (type != B200FFT_C2C && type != B200FFT_Z2Z) return B200FFT_INVALID_TYPE;
+  if (d * h * w == 0) return 0;
+  if (!in || !out) return B200FFT_INVALID_VALUE;
+  return b200fft::launch_centre(type == B200FFT_Z2Z, in, out, d, h, w, (cudaStream_t)stream) == cudaSuccess ? 0 : B200FFT_EXEC_FAILED;
+}
+// shift1D/2D/3D (Centre.hs:70-82,98-114,134-153: roll by n/2 + odd n) and ishift* (Centre.hs:84-96,116-132,155-164: n/2)
+int accfft_shift(int rank, const int64_t* shape, int type, int inverse, const void* in, void* out, b200fftStream stream) {
+  long long d, h, w;
+  if (int e = dims3(rank, shape, &d, &h, &w)) return e;
+  if (type != B200FFT_C2C && type != B200FFT_Z2Z) return B200FFT_INVALID_TYPE;
+  if (d * h * w == 0) return 0;
+  if (!in || !out || in == out) return B200FFT_INVALID_VALUE;
+  auto amount = [&](long long n) { return n / 2 + ((inverse || !(n & 1)) ? 0 : 1); };
+  return b200fft::launch_shift(type == B200FFT_Z2Z, in, out, d, h, w, amount(d), amount(h), amount(w), (cudaStream_t)stream) == cudaSuccess
+             ? 0 : B200FFT_EXEC_FAILED;
+}
+// shiftND (fftND mode x) in one go: kind 1/2/3 = fft1D/fft2D/fft3D.  Power-of-two extents: the rotation rides on the
+// stores of each axis' last butterfly pass (b200fftExecShifted: no extra pass over the array); otherwise the transform
+// goes to a pool buffer and the stand-alone shift follows.  Even extents: equals fftND mode (centreND x).
+int accfft_fft_centred(int kind, int mode, const int64_t* shape, int type, const void* in, void* out, b200fftStream stream) {
+  if (kind < 1 || kind > 3 || !shape) return B200FFT_INVALID_VALUE;
+  if (mode < Forward || mode > Inverse) return B200FFT_INVALID_VALUE;
+  if (type != B200FFT_C2C && type != B200FFT_Z2Z) return B200FFT_INVALID_TYPE;
+  long long d, h, w;
+  if (int e = dims3(kind, shape, &d, &h, &w)) return e;
+  if (d * h * w == 0) return 0;
+  Plans& ps = kind == 1 ? fft1D_plans : kind == 2 ? fft2D_plans : fft3D_plans;
+  b200fftHandle hnd = nullptr;
+  if (int e = with_plan(ps, d, h, w, type, &hnd)) return e;
+  const double scale = mode == Inverse ? 1.0 / ((double)d * (double)h * (double)w) : 1.0;
+  int e = b200fftExecShifted(hnd, in, out, fft_direction(mode), scale, stream);
+  if (e != B200FFT_NOT_SUPPORTED) return e;
+  void* tmp = nullptr;
+  const size_t bytes = (size_t)(d * h * w) * (type == B200FFT_Z2Z ? 16 : 8);
+  if (b200fft::pool_alloc(&tmp, bytes, (cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return B200FFT_ALLOC_FAILED; }
+  e = b200fftExecScaled(hnd, in, tmp, fft_direction(mode), scale, stream);
+  if (!e) e = accfft_shift(kind, shape, type, 0, tmp, out, stream);
+  cudaFreeAsync(tmp, (cudaStream_t)stream);
+  return e;
+}
+
 // One whole-array transform (or a chain of them) of a device-resident array on `stream`; src is preserved,
 // the result of the last transform lands in *result (either bufA or bufB, ping-pong).
 static int run_chain(int kind, const int* modes, int nmodes, int rank, const int64_t* shape, int type, const void* src, void* bufA,

@@ -161,6 +161,7 @@ struct Pass {
   Geom g{};
   GenericPass gp{};                // PK_GENERIC / PK_BLUESTEIN
   bool inplace_ok = false;         // reads and writes the same positions tile by tile
+  bool axis_last = false;          // the pass that produces an axis' final (natural-order) output index
   int src = BUF_IN, dst = BUF_OUT;
   void* tws = nullptr;             // device: stage twiddles
   void* tw_lo = nullptr;           // device: four-step twiddle tables
@@ -614,6 +615,11 @@ struct Builder {
 
   // ---- transform along one axis of an array viewed as [O][N][I] (I = element stride of the axis)
   void axis(long long O, long long N, long long I) {
+    const size_t before = p->passes.size();
+    axis_impl(O, N, I);
+    if (!err && p->passes.size() > before) p->passes.back().axis_last = true;
+  }
+  void axis_impl(long long O, long long N, long long I) {
     if (err || N == 1) return;
     if (O >= (1LL << 31) || I >= (1LL << 31) || N >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
     if (!is_pow2(N)) { generic_axis(O, N, I); return; }
@@ -722,6 +728,12 @@ struct Builder {
         if (!find_kernel(p->is_double, (int)n1, FL_COL, 1, 0)) continue;
         N1 = n1; N2 = cand; N3 = n3;
         break;
+      }
+    }
+    if (const char* sp = getenv("B200FFT_SPLIT3")) {   // developer override "n1,n2,n3"
+      long long a1 = 0, a2 = 0, a3 = 0;
+      if (sscanf(sp, "%lld,%lld,%lld", &a1, &a2, &a3) == 3 && a1 * a2 * a3 == N && is_pow2(a1) && is_pow2(a2) && is_pow2(a3)) {
+        N1 = a1; N2 = a2; N3 = a3; fuse_tail = false;
       }
     }
     long long M = N2 * N3;
@@ -995,7 +1007,24 @@ int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type
   return finish_plan(p, b, plan);
 }
 
+static int exec_common(b200fftHandle p, const void* in, void* out, int direction, double scale, bool shifted, b200fftStream stream_);
+
 int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
+  return exec_common(p, in, out, direction, scale, false, stream_);
+}
+
+// The transform followed by DFT/Centre.hs's shift1D/2D/3D along every transformed axis (zero frequency in the
+// middle), the rotation folded into the stores of each axis' last butterfly pass -- for even extents this is also
+// fft(centre(x)) (Centre.hs:17-19).  B200FFT_NOT_SUPPORTED when an axis' last pass is not a power-of-two line kernel
+// (odd / non-power-of-two extents): the caller then runs the stand-alone shift (accfft_fft_centred does).
+int b200fftExecShifted(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
+  if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
+  for (const Pass& ps : p->passes)
+    if (ps.axis_last && (ps.kind != PK_LINES || ps.k->N < 2 || (ps.k->N & 1))) return B200FFT_NOT_SUPPORTED;
+  return exec_common(p, in, out, direction, scale, true, stream_);
+}
+
+static int exec_common(b200fftHandle p, const void* in, void* out, int direction, double scale, bool shifted, b200fftStream stream_) {
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
   if (!in || !out || in == out) return B200FFT_INVALID_VALUE;
   if (direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) return B200FFT_INVALID_VALUE;
@@ -1025,7 +1054,8 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
     const bool first = i == 0, last = i + 1 == np;
     const double sc = last ? scale : 1.0;
     cudaError_t ce = cudaSuccess;
-    if (ps.pipe && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const bool rotate = shifted && ps.axis_last;
+    if (!rotate && ps.pipe && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
       Geom g = ps.g;
       g.swap_in = inverse && first;
       g.swap_out = inverse && last;
@@ -1053,7 +1083,14 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
       double scd = sc;
       void* args[] = {&g, (void*)&src, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
                       p->is_double ? (void*)&scd : (void*)&scf};
-      if (ps.ring && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      if (rotate) {   // output index k of this pass lands at (k + N/2) mod N: two "peers" = the two halves of the axis
+        const size_t esz = p->is_double ? 16 : 8;
+        g.npeers = 2;
+        g.peer_shift = ilog2(ps.k->N / 2);
+        g.peer[0] = (char*)dst + (size_t)(ps.k->N / 2) * (size_t)g.ons * esz;
+        g.peer[1] = dst;
+      }
+      if (!rotate && ps.ring && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
         g.ntl = ps.ring_ntl;
         ce = cudaLaunchKernel(ps.ring->func, dim3((unsigned)ps.ring_grid), dim3(ps.ring->threads), args, ps.ring->smem, stream);
       } else {

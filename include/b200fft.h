@@ -70,6 +70,12 @@ int b200fftExec(b200fftHandle plan, const void* in, void* out, int direction, b2
 int b200fftExecScaled(b200fftHandle plan, const void* in, void* out, int direction, double scale,
                       b200fftStream stream);
 
+/* The transform followed by DFT/Centre.hs's shift1D/2D/3D along every transformed axis, the half rotation folded into
+ * the stores of each axis' last butterfly pass (no extra pass).  Even extents: also
+ * fft(centre(x)) (Centre.hs:17-19).  B200FFT_NOT_SUPPORTED for extents that are not powers of two. */
+int b200fftExecShifted(b200fftHandle plan, const void* in, void* out, int direction, double scale,
+                       b200fftStream stream);
+
 /* FFT.destroy -- PTX/Plans.hs:80.  Safe from any thread (GC finaliser). */
 int b200fftDestroy(b200fftHandle plan);
 
@@ -130,6 +136,12 @@ int accfft_run_host(int kind, int mode, int rank, const int64_t* shape, int type
  * H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 overlap.  Pass pinned host buffers. */
 int accfft_run_host_seq(int kind, const int* modes, int nmodes, int rank, const int64_t* shape, int type,
                         const void* h_in, void* h_out);
+/* DFT/Centre.hs (rank 1..3): centre1D/2D/3D (:36-66), shift1D..3D and ishift1D..3D (:70-164; inverse != 0 selects the ishift family) as
+ * stand-alone passes, and shiftND(fftND mode x) in one call (kind 1/2/3) -- fused into the transform's last passes
+ * for power-of-two extents, transform + stand-alone shift otherwise. */
+int accfft_centre(int rank, const int64_t* shape, int type, const void* d_in, void* d_out, b200fftStream stream);
+int accfft_shift(int rank, const int64_t* shape, int type, int inverse, const void* d_in, void* d_out, b200fftStream stream);
+int accfft_fft_centred(int kind, int mode, const int64_t* shape, int type, const void* d_in, void* d_out, b200fftStream stream);
 /* when set non-zero the Inverse scale is fused into the last pass instead of a second kernel */
 void accfft_set_fused_inverse(int on);
 int accfft_plan_cache_size(void);

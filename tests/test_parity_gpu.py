@@ -301,6 +301,78 @@ def test_pipelined_kernels_default_policy_and_rows(af, dtype):
     assert rel_l2(y1, y0) <= bar(dtype, n) / 10
 
 
+# ---- DFT/Centre.hs: centre / shift / ishift and the fused shift(fft(x)) -------------------------------------------
+
+def _ref_shift(x, inverse):
+    """Centre.hs:70-164 restated: backpermute with roll i = (i + shift) rem n per axis."""
+    out = x
+    for ax, n in enumerate(x.shape):
+        sh = n // 2 + (0 if (inverse or n % 2 == 0) else 1)
+        out = np.take(out, (np.arange(n) + sh) % n, axis=ax)
+    return out
+
+
+def _ref_centre(x):
+    """Centre.hs:36-66 restated: (-1)^(sum of indices) * x."""
+    idx = np.indices(x.shape).sum(axis=0)
+    return np.where(idx % 2 == 0, x, -x)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_centre_shift_ishift_exact(af, dtype):
+    import torch
+    rng = np.random.default_rng(51)
+    for shape in [(1,), (2,), (7,), (8,), (1000,), (5, 6), (8, 3), (64, 64), (3, 4, 5), (8, 8, 8), (7, 1, 2)]:
+        x = rand_complex(rng, shape, dtype)
+        xd = torch.from_numpy(x).cuda()
+        r = len(shape)
+        c = getattr(af, "centre%dD" % r)(xd).cpu().numpy()
+        s = getattr(af, "shift%dD" % r)(xd).cpu().numpy()
+        i = getattr(af, "ishift%dD" % r)(xd).cpu().numpy()
+        assert np.array_equal(c, _ref_centre(x)), shape
+        assert np.array_equal(s, _ref_shift(x, False)) and np.array_equal(s, np.fft.fftshift(x)), shape
+        assert np.array_equal(i, _ref_shift(x, True)) and np.array_equal(i, np.fft.ifftshift(x)), shape
+        back = getattr(af, "ishift%dD" % r)(torch.from_numpy(s).cuda()).cpu().numpy()
+        assert np.array_equal(back, x), shape                       # Centre.hs:84-86
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_fft_centred_fused_and_fallback(af, oracle, dtype, mode):
+    """shift(fft(x)) in one call: for power-of-two extents the rotation is folded into the last pass of every axis (same
+    number of kernel launches as the plain transform); other extents take transform + stand-alone shift.  For even
+    extents it equals fft(centre(x)) (Centre.hs:17-19)."""
+    import torch
+    rng = np.random.default_rng(53)
+    shapes = [(2,), (64,), (4096,), (1 << 16,), (8, 16), (256, 64), (2048, 32), (4096, 64), (4, 8, 16), (64, 32, 128), (16, 2048, 8),
+              (1, 64), (64, 1), (6,), (1000,), (12, 10), (8, 7), (3, 4, 6)]
+    for shape in shapes:
+        x = rand_complex(rng, shape, dtype)
+        xd = torch.from_numpy(x).cuda()
+        kind = "fft%dD" % len(shape)
+        pow2 = all(n & (n - 1) == 0 for n in shape)
+        plain = getattr(af, kind)(mode, xd)
+        l0 = af.kernel_launches()
+        getattr(af, kind)(mode, xd)
+        l1 = af.kernel_launches()
+        y = af.fft_centred(mode, xd)
+        l2 = af.kernel_launches()
+        if pow2 and not (mode == "Inverse"):
+            assert l2 - l1 == l1 - l0, (shape, l1 - l0, l2 - l1)      # fused: no extra kernel
+        y = y.cpu().numpy()
+        ref = _ref_shift(plain.cpu().numpy(), False)
+        npts = x.size if len(shape) > 1 else shape[0]
+        assert rel_l2(y, ref) <= bar(dtype, npts) / 10, (shape, mode)
+        if pow2 and mode != "Inverse":
+            assert np.array_equal(y, ref), (shape, mode)              # same butterflies, permuted stores
+        if all(n % 2 == 0 for n in shape):
+            z = getattr(af, kind)(mode, getattr(af, "centre%dD" % len(shape))(xd)).cpu().numpy()
+            assert rel_l2(z, ref) <= bar(dtype, npts), (shape, mode)
+    x = rand_complex(rng, (64, 128), dtype)
+    y = af.fft_centred("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
+    assert rel_l2(y, _ref_shift(oracle.fft2D("Forward", x), False)) <= bar(dtype, x.size)
+
+
 SHAPES_3D = [(1, 1, 1), (2, 2, 2), (16, 32, 64), (64, 32, 16), (10, 12, 14), (3, 5, 7), (5, 64, 33), (4, 1024, 8), (1024, 4, 8),
              (64, 64, 64), (16, 16, 4096)]
 
