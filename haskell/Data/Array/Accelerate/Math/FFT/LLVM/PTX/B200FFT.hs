@@ -17,7 +17,7 @@ module Data.Array.Accelerate.Math.FFT.LLVM.PTX.B200FFT (
 
   Handle(..), Type(..), Mode(..), B200FFTException(..),
   plan1D, plan2D, plan3D, planMany,
-  execC2C, execZ2Z, execC2CScaled, execZ2ZScaled,
+  execC2C, execZ2Z, execC2CScaled, execZ2ZScaled, execC2CShifted, execZ2ZShifted,
   destroy,
 
 ) where
@@ -72,6 +72,7 @@ foreign import ccall safe   "b200fftPlanMany1d" c_planMany1d :: Ptr (Ptr ()) -> 
 -- exec only enqueues kernels on the stream and never blocks: unsafe call is appropriate
 foreign import ccall unsafe "b200fftExec"       c_exec       :: Ptr () -> Ptr () -> Ptr () -> CInt -> Ptr () -> IO CInt
 foreign import ccall unsafe "b200fftExecScaled" c_execScaled :: Ptr () -> Ptr () -> Ptr () -> CInt -> CDouble -> Ptr () -> IO CInt
+foreign import ccall unsafe "b200fftExecShifted" c_execShifted :: Ptr () -> Ptr () -> Ptr () -> CInt -> CDouble -> Ptr () -> IO CInt
 foreign import ccall safe   "b200fftDestroy"    c_destroy    :: Ptr () -> IO CInt
 foreign import ccall unsafe "b200fftErrorString" c_errorString :: CInt -> IO CString
 
@@ -127,6 +128,14 @@ execScaled (Handle h) dir s (Stream st) (DevicePtr i) (DevicePtr o) =
 execC2CScaled, execZ2ZScaled :: Handle -> Mode -> Double -> Stream -> DevicePtr a -> DevicePtr a -> IO ()
 execC2CScaled = execScaled
 execZ2ZScaled = execScaled
+
+-- | The transform followed by DFT/Centre.hs's shift1D/2D/3D (zero frequency in the middle), the half rotation folded
+-- into the stores of the last butterfly pass of every axis (SURVEY.md 8f-4); power-of-two extents only -- other
+-- extents raise B200FFTException NOT_SUPPORTED and the caller composes `shiftND . fftND` as today.
+execC2CShifted, execZ2ZShifted :: Handle -> Mode -> Double -> Stream -> DevicePtr a -> DevicePtr a -> IO ()
+execC2CShifted (Handle h) dir s (Stream st) (DevicePtr i) (DevicePtr o) =
+  check =<< c_execShifted h (castPtr i) (castPtr o) (fromIntegral (fromEnum dir)) (realToFrac s) (castPtr st)
+execZ2ZShifted = execC2CShifted
 
 -- | FFT.destroy                                           (PTX/Plans.hs:80)
 -- Safe from a GC finaliser thread; a status other than success is ignored there.
