@@ -7,8 +7,8 @@ void register_f32_col(void (*add)(const KernelEntry&)) {
   REG_COL(float, 8, 8, 128, 0, 8);
   REG_COL(float, 16, 16, 128, 0, 16);
   REG_COL(float, 32, 8, 32, 0, 8, 4);
-  REG_COL(float, 64, 8, 16, 0, 8, 8);
-  REG_COL(float, 64, 16, 32, 0, 16, 4);               // v1: 32 lines (256 B runs), 16 KB tiles
+  REG_COL(float, 64, 16, 32, 0, 16, 4);               // v0: 32 lines (256 B runs), 16 loads in flight per thread (cfg3: 556 -> 537 us)
+  REG_COL(float, 64, 8, 16, 0, 8, 8);                 // v1: 16 lines; latency-bound (ncu: long_scoreboard 12.8 per issue)
   REG_COL(float, 128, 16, 32, 0, 16, 8);               // v0: 256 B runs (99-103 % of the copy peak; 95 % with 128 B runs at 4 MB row stride)
   REG_COL(float, 128, 16, 16, 0, 16, 8);               // v1: 128 B runs -- taken when the axis has fewer than 32 columns
   REG_COL(float, 128, 16, 8, 0, 16, 8);                // v2: 64 B runs

@@ -664,6 +664,10 @@ struct Builder {
     long long N1, N2;
     // small sub-lengths keep the [N][TL] tiles small; cap at 1024 so TL stays >= 8
     if (!split2(N, 1024, &N1, &N2)) { err = B200FFT_NOT_SUPPORTED; return; }
+    if (const char* sp = getenv("B200FFT_SPLIT2")) {   // developer override "n1,n2"
+      long long a1 = 0, a2 = 0;
+      if (sscanf(sp, "%lld,%lld", &a1, &a2) == 2 && a1 * a2 == N && is_pow2(a1) && is_pow2(a2)) { N1 = a1; N2 = a2; }
+    }
     if (N2 * I >= (1LL << 31) || O * N1 >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
     {  // pass A: FFT over n1, lines = (n2,i), twiddle w_N^(k1*n2), same positions
       Geom g{};
