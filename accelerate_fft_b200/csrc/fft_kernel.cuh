@@ -74,8 +74,11 @@ struct Cfg {
   static constexpr int XPAD = (TL < GROUP) ? TL : 0;
   static constexpr int COL_ELEMS = N * TL + ((N - 1) >> LOGQ) * XPAD + TL;
   static constexpr int ROW_ELEMS = PITCH * TL;
+  // single register stage, one whole line per thread: contiguous rows are staged through shared memory so that the
+  // global loads / stores are coalesced (fft_small_rows_tile), pitch N + 1
+  static constexpr bool SMALL_ROWS = (S == 1) && (TPT == 1) && (N >= 2);
   template <bool COL> static constexpr size_t smem_bytes() {
-    return (S > 1) ? (size_t)(COL ? COL_ELEMS : ROW_ELEMS) * ESZ : 0;
+    return (S > 1) ? (size_t)(COL ? COL_ELEMS : ROW_ELEMS) * ESZ : (!COL && SMALL_ROWS) ? (size_t)TL * (N + 1) * ESZ : 0;
   }
 };
 
@@ -309,6 +312,50 @@ __device__ __forceinline__ void fft_lines_tile(const Geom& g, unsigned tile, con
   }
 }
 
+// Rows of 2..16 points, one line per thread: a thread's points are N*sizeof(C) bytes apart from its neighbour's, so direct
+// loads touch 32 different 128 B lines per instruction (c64 n=16: 30 % of HBM peak).  Contiguous rows go through shared
+// memory instead: the CTA's TL*N-element chunk is loaded and stored with unit stride across threads.
+template <class K>
+__device__ __forceinline__ void fft_small_rows_tile(const Geom& g, unsigned tile, const cpx_t<typename K::real>* __restrict__ in,
+                                                    cpx_t<typename K::real>* __restrict__ out, typename K::real scale,
+                                                    cpx_t<typename K::real>* sm) {
+  using T = typename K::real;
+  using C = cpx_t<T>;
+  constexpr int N = K::N, TL = K::TL, LG = K::ilog2(N);
+  const int tid = threadIdx.x;
+  int lt, o, b;
+  if (g.no == 1 && g.nb == 1) { lt = (int)tile; o = 0; b = 0; }
+  else {
+    lt = tile % (unsigned)g.ntl;
+    const unsigned rest = tile / (unsigned)g.ntl;
+    o = rest % (unsigned)g.no;
+    b = rest / (unsigned)g.no;
+  }
+  const long long line0 = (long long)lt * TL;
+  const int nvalid = (int)(((long long)g.nl - line0 < TL ? (long long)g.nl - line0 : (long long)TL) * N);
+  const C* ip = in + (long long)b * g.ibs + (long long)o * g.ios + line0 * N;
+  C* op = out + (long long)b * g.obs + (long long)o * g.oos + line0 * N;
+  static_for<0, N>([&](auto ic) {
+    constexpr int i = ic;
+    const int idx = tid + i * TL;
+    if (idx < nvalid) sm[idx + (idx >> LG)] = ld_stream(ip + idx);
+  });
+  __syncthreads();
+  C v[N];
+  static_for<0, N>([&](auto ec) { constexpr int e = ec; v[e] = sm[tid * (N + 1) + e]; });
+  if (g.swap_in) static_for<0, N>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
+  dft<N>(v);
+  const T sy = g.swap_out ? -scale : scale;
+  if (scale != (T)1 || g.swap_out) static_for<0, N>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
+  static_for<0, N>([&](auto ec) { constexpr int e = ec; sm[tid * (N + 1) + e] = v[e]; });
+  __syncthreads();
+  static_for<0, N>([&](auto ic) {
+    constexpr int i = ic;
+    const int idx = tid + i * TL;
+    if (idx < nvalid) st_stream(op + idx, sm[idx + (idx >> LG)]);
+  });
+}
+
 template <class K, bool LLF, bool SLF, bool TW4, bool PRE2 = false>
 __global__ void __launch_bounds__(K::THREADS, K::MINB)
 fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
@@ -316,6 +363,12 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
                  const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale) {
   using C = cpx_t<typename K::real>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if constexpr (!LLF && !SLF && !TW4 && !PRE2 && K::SMALL_ROWS) {
+    if (g.ils == K::N && g.ols == K::N && g.ins == 1 && g.ons == 1 && g.npeers == 0) {   // CTA-uniform
+      fft_small_rows_tile<K>(g, blockIdx.x, in, out, scale, reinterpret_cast<C*>(smem_raw));
+      return;
+    }
+  }
   fft_lines_tile<K, LLF, SLF, TW4, false, 0, PRE2>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
 }
 
