@@ -210,3 +210,113 @@ fft_cluster_cols_kernel(const Geom g, const cpx_t<typename CC::K::real>* __restr
 }
 
 }  // namespace b200fft
+
+namespace b200fft {
+
+// ---- rows + the first radix-CS stage of a strided axis, in one pass -------------------------------------------------
+// A 2D transform [H][W] whose column axis is too long for one pass (H = CS*M) normally costs rows + two column passes.
+// Here a cluster of CS CTAs takes the CS rows {n2 + M*n1} (n1 = CTA rank): every CTA transforms its row along W with
+// the ordinary row stages, then the cluster does the radix-CS butterflies ACROSS the rows (the first four-step stage of
+// the column axis, n = n1*M + n2) -- rank c collects columns [c*W/CS, (c+1)*W/CS) of all CS rows through distributed
+// shared memory (register e goes to CTA e/(E/CS): compile-time), butterflies over n1, multiplies by w_H^(k1*n2) (one
+// constant per output row) and stores W/CS contiguous elements of each of the CS rows k1*M + n2.  What is left of the
+// column axis is ONE M-point pass over consecutive rows (stride W, index-reversed store k1 + CS*k2).
+template <class K_, int CS_>
+struct ClusterRowCfg {
+  using K = K_;
+  static constexpr int CS = CS_;
+  static constexpr int EP = K::E / CS_;          // phase-2 butterflies per thread
+  static constexpr int CH = K::N / CS_;          // columns owned by one CTA in phase 2
+  static_assert(K::TL == 1 && K::S >= 2, "one contiguous row per CTA");
+  static_assert(K::E % CS_ == 0 && (CS_ == 2 || CS_ == 4 || CS_ == 8 || CS_ == 16), "cluster size = register radix across the rows");
+  static constexpr int SM_ELEMS = K::ROW_ELEMS > K::N ? K::ROW_ELEMS : K::N;
+  static constexpr size_t SMEM = (size_t)SM_ELEMS * K::ESZ;
+};
+
+// Geom: row (b, n1, n2) of the input at b*ibs + n1*ios + n2*ils (W contiguous elements, ins == 1); same for the output
+// with obs / oos / ols.  g.nl = M (clusters per batch entry), g.nb = batch.  ctw[(k1-1)*M + n2] = w_H^(k1*n2).
+template <class CC>
+__global__ void __launch_bounds__(CC::K::THREADS, CC::K::MINB)
+fft_cluster_rows_kernel(const Geom g, const cpx_t<typename CC::K::real>* __restrict__ in, cpx_t<typename CC::K::real>* __restrict__ out,
+                        const cpx_t<typename CC::K::real>* __restrict__ tws, const cpx_t<typename CC::K::real>* __restrict__,
+                        const cpx_t<typename CC::K::real>* __restrict__, typename CC::K::real scale,
+                        const cpx_t<typename CC::K::real>* __restrict__ ctw) {
+  using K = typename CC::K;
+  using T = typename K::real;
+  using C = cpx_t<T>;
+  constexpr int CS = CC::CS, EP = CC::EP, CH = CC::CH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* sm = reinterpret_cast<C*>(smem_raw);
+
+  const int t = threadIdx.x;
+  const unsigned rank = cluster_ctarank();
+  const unsigned tile = cluster_id_x();
+  const int n2 = (int)(tile % (unsigned)g.nl), b = (int)(tile / (unsigned)g.nl);
+
+  // ---- phase 1: this CTA's row along W ---------------------------------------------------------------
+  C v[K::E];
+  {
+    const C* ip = in + (long long)b * g.ibs + (long long)rank * g.ios + (long long)n2 * g.ils + t;
+    auto head = [&](auto cj) {
+      constexpr bool CJ = decltype(cj)::value;
+      static_for<0, K::E>([&](auto ec) {
+        constexpr int e = ec;
+        C x = ld_stream(ip + e * K::TPT);
+        if constexpr (CJ) x.y = -x.y;
+        v[e] = x;
+      });
+      run_stage<K, 0>(v, t, tws);
+      scatter<K, 0, false>(v, sm, 0, t);
+    };
+    if (g.swap_in) head(std::true_type{}); else head(std::false_type{});
+  }
+  static_for<1, K::S - 1>([&](auto sc) {
+    constexpr int s = sc;
+    __syncthreads();
+    gather<K, false>(v, sm, 0, t);
+    run_stage<K, s>(v, t, tws);
+    __syncthreads();
+    scatter<K, s, false>(v, sm, 0, t);
+  });
+  __syncthreads();
+  gather<K, false>(v, sm, 0, t);
+  run_stage<K, K::S - 1>(v, t, tws);      // v[e] = X[kx = t + e*TPT] of row n1 = rank
+  cluster_arrive_relaxed();               // this CTA no longer reads its exchange space
+
+  // ---- exchange: columns [c*CH, (c+1)*CH) = registers [c*EP, (c+1)*EP) go to CTA c, slot [rank][(e % EP)*TPT + t] ----
+  cluster_wait();
+  {
+    const uint32_t base = smem_u32(sm) + (uint32_t)((int)rank * CH + t) * (uint32_t)sizeof(C);
+    static_for<0, CS>([&](auto dc) {
+      constexpr int d = dc;
+      const uint32_t ra = map_to_rank(base, (unsigned)d);
+      static_for<0, EP>([&](auto jc) {
+        constexpr int j = jc;
+        st_cluster(ra + (uint32_t)(j * K::TPT) * (uint32_t)sizeof(C), v[d * EP + j]);
+      });
+    });
+  }
+  cluster_arrive();
+  cluster_wait();
+
+  // ---- phase 2: radix-CS over n1 for columns rank*CH + t + j*TPT, twiddle w_H^(k1*n2), rows k1*M + n2 -----------
+  {
+    C w[CS];
+    w[0] = C{(T)1, (T)0};
+    static_for<1, CS>([&](auto kc) { constexpr int k1 = kc; w[k1] = __ldg(ctw + (size_t)(k1 - 1) * g.nl + n2); });
+    C* op = out + (long long)b * g.obs + (long long)n2 * g.ols + (long long)rank * CH + t;
+    const T sy = g.swap_out ? -scale : scale;
+    const bool post = (scale != (T)1) || g.swap_out;
+    static_for<0, EP>([&](auto jc) {
+      constexpr int j = jc;
+      C a[CS];
+      static_for<0, CS>([&](auto nc) { constexpr int n1 = nc; a[n1] = sm[n1 * CH + j * K::TPT + t]; });
+      dft<CS>(a);
+      static_for<1, CS>([&](auto kc) { constexpr int k1 = kc; a[k1] = cmul(a[k1], w[k1]); });
+      if (post) static_for<0, CS>([&](auto kc) { constexpr int k1 = kc; a[k1].x *= scale; a[k1].y *= sy; });
+      static_for<0, CS>([&](auto kc) { constexpr int k1 = kc; op[(long long)k1 * g.oos + j * K::TPT] = a[k1]; });
+    });
+  }
+}
+
+}  // namespace b200fft

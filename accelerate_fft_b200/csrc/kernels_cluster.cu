@@ -22,6 +22,24 @@ KernelEntry make_cluster_entry() {
   return e;
 }
 
+template <class CC>
+KernelEntry make_cluster_row_entry() {
+  using K = typename CC::K;
+  KernelEntry e{};
+  e.is_double = sizeof(typename K::real) == 8;
+  e.N = K::N; e.N1 = K::N; e.CS = CC::CS; e.E = K::E; e.TL = 1;
+  e.S = K::S;
+  for (int i = 0; i < 4; i++) e.rad[i] = K::rad[i];
+  e.tw_len = K::TW_LEN;
+  e.flavor = FL_CLUSTERROW;
+  e.threads = K::THREADS;
+  e.smem = CC::SMEM;
+  e.minb = K::MINB;
+  e.func = reinterpret_cast<const void*>(&fft_cluster_rows_kernel<CC>);
+  return e;
+}
+#define REG_CLUSTER_ROWS(CS, ...) add(make_cluster_row_entry<ClusterRowCfg<Cfg<__VA_ARGS__>, CS>>())
+
 #define REG_CLUSTER(CS, ...) add(make_cluster_entry<ClusterCfg<Cfg<__VA_ARGS__>, CS>, false>())
 
 void register_cluster(void (*add)(const KernelEntry&)) {
@@ -39,6 +57,10 @@ void register_cluster(void (*add)(const KernelEntry&)) {
   // c64 N = 16384
   REG_CLUSTER(8, float, 2048, 32, 8, 1, 32, 16, 4);       // v0: 512 thr, 64 B runs, 128 KB
   REG_CLUSTER(16, float, 1024, 32, 8, 2, 32, 32);         // v1: cluster of 16, 64 KB
+  // rows of W points + the first radix-8 stage of the column axis (2D transforms with H = 8*M)
+  REG_CLUSTER_ROWS(8, float, 8192, 32, 1, 2, 32, 16, 16);   // cfg3
+  REG_CLUSTER_ROWS(8, float, 4096, 16, 1, 2, 16, 16, 16);
+  REG_CLUSTER_ROWS(8, double, 4096, 16, 1, 2, 16, 16, 16);
   // c128 N = 4096 / 8192
   REG_CLUSTER(8, double, 512, 16, 8, 2, 16, 16, 2);       // 256 thr x 128 regs, 128 B runs, 64 KB
   REG_CLUSTER(8, double, 1024, 16, 4, 2, 16, 16, 4);      // 256 thr, 64 B runs, 64 KB

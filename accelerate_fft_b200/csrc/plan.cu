@@ -808,6 +808,56 @@ struct Builder {
     return true;
   }
 
+  // ---- 2D [H][W], H = CS*M: rows + the first radix-CS stage of the column axis in one cluster pass, then ONE M-point
+  //      column pass over consecutive rows (cluster_kernel.cuh: fft_cluster_rows_kernel) ------------------------------
+  bool try_cluster_rows_2d(long long H, long long W) {
+    const char* mode = getenv("B200FFT_CLUSTER_ROWS");
+    if (!(mode && atoi(mode))) return false;
+    if (!is_pow2(H) || !is_pow2(W) || H <= max_col_n()) return false;
+    const KernelEntry* k = find_kernel(p->is_double, (int)W, FL_CLUSTERROW, 0, 0);
+    if (!k || H % k->CS) return false;
+    const long long M = H / k->CS;
+    if (M > max_col_n() || M < 2 || !find_kernel(p->is_double, (int)M, FL_COL, 0, (int)W)) return false;
+    if (H * W >= (1LL << 40)) return false;
+    {
+      Pass ps;
+      ps.kind = PK_CLUSTER;
+      ps.k = k;
+      Geom g{};
+      g.nb = 1; g.no = 1; g.nl = (int)M; g.ntl = (int)M;
+      g.ios = M * W; g.ils = W; g.ins = 1;
+      g.oos = M * W; g.ols = W; g.ons = 1;
+      g.tw_div = 1;
+      ps.g = g;
+      ps.inplace_ok = true;
+      ps.ntiles = M;
+      ps.tws = make_stage_twiddles(p, k);
+      auto build = [&](auto tag) -> void* {   // w_H^(k1 * n2), k1 = 1 .. CS-1, n2 < M
+        using T = decltype(tag);
+        std::vector<T> h(2 * (size_t)(k->CS - 1) * M);
+        for (int k1 = 1; k1 < k->CS; k1++)
+          for (long long n2 = 0; n2 < M; n2++) fill_root_table(h, (size_t)(k1 - 1) * M + n2, (long long)k1 * n2, H);
+        return upload(p, h);
+      };
+      ps.ctw = p->is_double ? build(double{}) : build(float{});
+      char buf[256];
+      snprintf(buf, sizeof buf, "rows+radix%d: cluster rows N=%d E=%d radix=%dx%dx%dx%d | %d CTAs x threads=%d smem=%zu clusters=%lld", k->CS,
+               k->N, k->E, k->rad[0], k->rad[1], k->rad[2], k->rad[3], k->CS, k->threads, k->smem, (long long)M);
+      ps.desc = buf;
+      push(ps);
+    }
+    {  // the M-point transforms over n2 for each k1 (consecutive rows), output row k1 + CS*k2
+      Geom g{};
+      g.nb = 1; g.no = k->CS; g.nl = (int)W;
+      g.ios = M * W; g.ils = 1; g.ins = W;
+      g.oos = W; g.ols = 1; g.ons = (long long)k->CS * W;
+      g.tw_div = 1;
+      if (!lines_pass((int)M, FL_COL, false, g, 0, false, 0, "cols-tail")) { err = B200FFT_INTERNAL_ERROR; return true; }
+      p->passes.back().axis_last = true;
+    }
+    return true;
+  }
+
   // ---- arbitrary (non power-of-two) axis lengths: generic_kernel.cu -----------------------
   void generic_axis(long long O, long long N, long long I) {
     Pass ps;
@@ -989,7 +1039,7 @@ int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type) {
   auto* p = new b200fft_plan_s;
   p->is_double = dbl; p->rank = 2; p->dims[0] = h; p->dims[1] = w; p->total = h * w;
   Builder b{p};
-  if (!b.try_pair_2d(h, w)) {
+  if (!b.try_cluster_rows_2d(h, w) && !b.try_pair_2d(h, w)) {
     b.axis(h, w, 1);   // rows
     b.axis(1, h, w);   // columns
   }

@@ -228,6 +228,30 @@ def test_cluster_column_kernel(af, oracle, dtype, mode):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", MODES)
+def test_cluster_rows_plus_first_column_stage(af, oracle, dtype, mode):
+    """2D with H = 8*M: rows + the radix-8 first stage of the column axis in one cluster pass (exchange across the 8 rows
+    through distributed shared memory), then ONE M-point column pass (cluster_kernel.cuh fft_cluster_rows_kernel;
+    opt-in, B200FFT_CLUSTER_ROWS=1 -- measured slower than the three-pass plan, profiles/r01_pipe_and_cluster.txt)."""
+    rng = np.random.default_rng(45)
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    shapes = [(4096, 4096), (8192, 4096)] if mode != "Reverse" else [(4096, 4096)]
+    with _env(af, B200FFT_CLUSTER_ROWS="1"):
+        for shape in shapes:
+            p = af.Plan("2d", list(shape), typ, 1)
+            d = p.describe()
+            p.destroy()
+            assert "rows+radix8" in d and len(d.strip().split("\n")) == 2, d
+            x = rand_complex(rng, shape, dtype)
+            y = gpu(af, "fft2D", mode, x)
+            assert rel_l2(y, _np_fft2(mode, x)) <= bar(dtype, x.size), (shape, mode)
+    x = rand_complex(rng, (4096, 4096), dtype)
+    with _env(af, B200FFT_CLUSTER_ROWS="1"):
+        y = gpu(af, "fft2D", "Forward", x)
+    assert rel_l2(y, oracle.fft2D("Forward", x, threads=8)) <= bar(dtype, x.size)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode", ["Forward", "Inverse"])
 def test_pipelined_column_kernels(af, oracle, dtype, mode):
     """The persistent software-pipelined column kernel (pipe_kernel.cuh): cp.async landing FIFO, two thread groups and,
