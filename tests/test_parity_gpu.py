@@ -397,6 +397,37 @@ def test_fft_centred_fused_and_fallback(af, oracle, dtype, mode):
     assert rel_l2(y, _ref_shift(oracle.fft2D("Forward", x), False)) <= bar(dtype, x.size)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_exec_scatter_single_gpu(af, dtype):
+    """b200fftExecScatter on one device: the stores of a strided-axis pass split by output index over several buffers
+    (the slab transform's exchange; with peer-mapped buffers in tests/test_multigpu.py).  Both the lock-step kernel
+    (several targets) and the pipelined one (single target, transposing store) against the plain exec."""
+    import torch
+    rng = np.random.default_rng(61)
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    for (outer, n, inner, npeers) in [(6, 64, 40, 4), (3, 1024, 96, 8), (2, 1024, 96, 1), (1, 2048, 64, 2)]:
+        x = rand_complex(rng, (outer, n, inner), dtype)
+        xd = torch.from_numpy(x).cuda()
+        ref = torch.empty_like(xd)
+        with _env(af, B200FFT_PIPE_MIN_TILES="1"):
+            p = af.Plan("axis", [outer, n, inner], typ, 1)
+            p.exec(xd, ref, af.FORWARD)
+            nl = n // npeers
+            outs = [torch.zeros((outer, nl, inner), dtype=xd.dtype, device="cuda") for _ in range(npeers)]
+            p.exec_scatter(xd, [o.data_ptr() for o in outs], nl * inner, inner, af.FORWARD)
+            torch.cuda.synchronize()
+            for r in range(npeers):
+                # (the plain exec of N=2048 c64 takes the cluster-of-2 pipelined kernel: same values, different rounding)
+                assert rel_l2(outs[r].cpu().numpy(), ref[:, r * nl:(r + 1) * nl, :].cpu().numpy()) <= bar(dtype, n) / 20, (outer, n, inner, npeers, r)
+            if npeers == 1:   # transposing store: (o, k, i) -> [k][o][i]
+                tr = torch.zeros((n, outer, inner), dtype=xd.dtype, device="cuda")
+                p.exec_scatter(xd, [tr.data_ptr()], inner, outer * inner, af.FORWARD)
+                torch.cuda.synchronize()
+                assert rel_l2(tr.cpu().numpy(), ref.transpose(0, 1).contiguous().cpu().numpy()) <= bar(dtype, n) / 20
+            p.destroy()
+    assert rel_l2(ref.cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=1)) <= bar(dtype, 2048)
+
+
 SHAPES_3D = [(1, 1, 1), (2, 2, 2), (16, 32, 64), (64, 32, 16), (10, 12, 14), (3, 5, 7), (5, 64, 33), (4, 1024, 8), (1024, 4, 8),
              (64, 64, 64), (16, 16, 4096)]
 
