@@ -262,12 +262,19 @@ def test_pipelined_column_kernels(af, oracle, dtype, mode):
     typ = af.C2C if dtype == np.complex64 else af.Z2Z
     n1 = 1024 if dtype == np.complex64 else 512          # the CTA share of the instantiated kernels
     with _env(af, B200FFT_CLUSTER="1", B200FFT_PIPE="1", B200FFT_PIPE_MIN_TILES="1"):
-        for cs, inner in [(1, 64), (1, 8 * 148 * 3 + 8), (2, 128), (4, 64), (8, 64), (8, 8 * 37), (16, 128)]:
-            shape = (n1 * cs, inner)
+        cases = [(1, 64), (1, 8 * 148 * 3 + 8), (2, 128), (4, 64), (8, 64), (8, 8 * 37), (16, 128)]
+        for cs, inner in cases + ([(0, 256)] if dtype == np.complex64 else []):
+            shape = (n1 * cs, inner) if cs else (512, inner)       # cs == 0: the c64 512-point single-CTA kernel
             p = af.Plan("2d", list(shape), typ, 1)
             d = p.describe()
             p.destroy()
-            assert "pipe: N=%dx%d" % (n1, cs) in d, d
+            if cs == 0:
+                want = "pipe: N=512x1"
+            elif dtype == np.complex128 and cs == 2:
+                want = "pipe: N=1024x1"                            # c128 N=1024: one CTA with 4 columns is the default
+            else:
+                want = "pipe: N=%dx%d" % (n1, cs)
+            assert want in d, d
             x = rand_complex(rng, shape, dtype)
             y = gpu(af, "fft2D", mode, x)
             assert rel_l2(y, _np_fft2(mode, x)) <= bar(dtype, x.size), (shape, mode)
@@ -301,8 +308,11 @@ def test_pipelined_kernels_default_policy_and_rows(af, dtype):
     rng = np.random.default_rng(47)
     typ = af.C2C if dtype == np.complex64 else af.Z2Z
     n1 = 1024 if dtype == np.complex64 else 512
+    p = af.Plan("axis", [16, 1024, 512], typ, 1)
+    assert "pipe: N=1024x1" in p.describe(), p.describe()          # both types: N=1024 in one CTA
+    p.destroy()
     p = af.Plan("axis", [16, n1, 512], typ, 1)
-    assert ("pipe:" in p.describe()) == (dtype == np.complex64), p.describe()      # c128 stays on the lock-step kernel
+    assert ("pipe:" in p.describe()) == (dtype == np.complex64), p.describe()      # c128 N=512 stays on the lock-step kernel
     x = rand_complex(rng, (16, n1, 512), dtype)
     xd = torch.from_numpy(x).cuda()
     yd = torch.empty_like(xd)
