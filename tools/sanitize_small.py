@@ -33,4 +33,19 @@ for dt, n1 in ((np.complex64, 1024), (np.complex128, 512)):
     run("fft3D", (16, 32, 64), dt)
 run("fft", (301, 8192), np.complex64, B200FFT_PIPE="1")           # pipe rows
 run("fft", (5, 1000), np.complex64); run("fft", (5, 1009), np.complex64)   # mixed radix, Bluestein
+for dt in (np.complex64, np.complex128):
+    for n in (2, 4, 8, 16, 32):
+        run("fft", (1000, n), dt)                                 # rows staged through shared memory (ragged last tile)
+    run("fft2D", (4096, 64), dt, B200FFT_CLUSTER_ROWS="0")
+    run("fft2D", (4096, 4096), dt, B200FFT_CLUSTER_ROWS="1")      # rows + first radix-8 column stage in a cluster
+    run("fft2D", (1024, 2048), dt)                                # default policy: pipelined N=1024 column pass
+    x = (rng.uniform(-1, 1, (64, 32, 128)) + 1j * rng.uniform(-1, 1, (64, 32, 128))).astype(dt)
+    y = af.fft_centred("Forward", torch.from_numpy(x).cuda()).cpu().numpy()          # rotation folded into the last passes
+    assert np.linalg.norm(y - np.fft.fftshift(np.fft.fftn(x.astype(np.complex128)))) / np.linalg.norm(y) < 1e-4
+    p = af.Plan("axis", (3, 1024, 96), af.C2C if dt == np.complex64 else af.Z2Z)
+    xd = torch.from_numpy((rng.uniform(-1, 1, (3, 1024, 96)) + 0j).astype(dt)).cuda()
+    outs = [torch.zeros((3, 128, 96), dtype=xd.dtype, device="cuda") for _ in range(8)]
+    p.exec_scatter(xd, [o.data_ptr() for o in outs], 128 * 96, 96, af.FORWARD)        # scatter store
+    torch.cuda.synchronize(); p.destroy()
+    print("centred + scatter ok", np.dtype(dt).name, flush=True)
 print("ok")
