@@ -198,6 +198,7 @@ struct b200fft_plan_s {
   size_t scratch_bytes = 0;   // main scratch (same size as the array) if any pass uses BUF_SCRATCH
   size_t extra_bytes = 0;     // bluestein workspace
   size_t band_bytes = 0;      // fused passes: two L2-resident band slots + the ticket / progress counters
+  bool no_shift = false;      // built by a whole-transform builder that does not mark the axes' last passes (b200fftExecShifted)
 };
 
 namespace b200fft {
@@ -594,6 +595,7 @@ struct Builder {
 
   // x rows + y columns of each z-plane of a [D][H][W] array, the plane staying in L2 between the two
   bool try_fused_plane(long long D, long long H, long long W) {
+    struct Mark { b200fft_plan_s* p; size_t n0; ~Mark() { if (p->passes.size() > n0) p->no_shift = true; } } mark{p, p->passes.size()};
     if (!is_pow2(H) || !is_pow2(W) || D >= (1LL << 24)) return false;
     const FusedEntry* fz = find_fused(p->is_double, (int)W, FL_ROW, 0, (int)H, FL_COL);
     if (!fz) return false;
@@ -778,6 +780,7 @@ struct Builder {
   // x[n2] + (-1)^k1 x[n2+M] along W, multiplies by w_H^(k1*n2) (one constant per row) and stores row 2*n2 + k1.
   // Pass 2 is the M-point column transform over n2 of the rows of parity k1, in place (k2 lands on row k1 + 2*k2).
   bool try_pair_2d(long long H, long long W) {
+    struct Mark { b200fft_plan_s* p; size_t n0; ~Mark() { if (p->passes.size() > n0) p->no_shift = true; } } mark{p, p->passes.size()};
     // Opt-in (B200FFT_PAIR2D=1).  Measured on B200 (profiles/r01_pair2d_and_narrow_columns.txt): correct, but the
     // column pass it needs -- 4096-point columns in tiles only 2-4 columns wide (16-32 B runs) -- reaches just
     // 2.5 TB/s, so cfg3 takes 693 us with it against 562 us for rows + two wide-tile column passes.
@@ -812,6 +815,7 @@ struct Builder {
   // ---- 2D [H][W], H = CS*M: rows + the first radix-CS stage of the column axis in one cluster pass, then ONE M-point
   //      column pass over consecutive rows (cluster_kernel.cuh: fft_cluster_rows_kernel) ------------------------------
   bool try_cluster_rows_2d(long long H, long long W) {
+    struct Mark { b200fft_plan_s* p; size_t n0; ~Mark() { if (p->passes.size() > n0) p->no_shift = true; } } mark{p, p->passes.size()};
     const char* mode = getenv("B200FFT_CLUSTER_ROWS");
     if (!(mode && atoi(mode))) return false;
     if (!is_pow2(H) || !is_pow2(W) || H <= max_col_n()) return false;
@@ -1076,6 +1080,7 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
 // (odd / non-power-of-two extents): the caller then runs the stand-alone shift (accfft_fft_centred does).
 int b200fftExecShifted(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
+  if (p->no_shift) return B200FFT_NOT_SUPPORTED;
   for (const Pass& ps : p->passes)
     if (ps.axis_last && (ps.kind != PK_LINES || ps.k->N < 2 || (ps.k->N & 1))) return B200FFT_NOT_SUPPORTED;
   return exec_common(p, in, out, direction, scale, true, stream_);

@@ -405,6 +405,11 @@ def test_fft_centred_fused_and_fallback(af, oracle, dtype, mode):
     x = rand_complex(rng, (64, 128), dtype)
     y = af.fft_centred("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
     assert rel_l2(y, _ref_shift(oracle.fft2D("Forward", x), False)) <= bar(dtype, x.size)
+    # plans built by the whole-transform builders do not carry the rotation: the call must fall back, not mis-shift
+    with _env(af, B200FFT_CLUSTER_ROWS="1", B200FFT_PAIR2D="1"):
+        x = rand_complex(rng, (4096, 4096), dtype)
+        y = af.fft_centred("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
+        assert rel_l2(y, np.fft.fftshift(np.fft.fft2(x.astype(np.complex128)))) <= bar(dtype, x.size)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
