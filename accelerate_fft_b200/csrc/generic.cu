@@ -73,10 +73,38 @@ struct MixedParams {
   long long O, N, I;
   int nstages;
   int radix[12];
-  int TL;
-  int line_fast;  // 1: adjacent threads load adjacent lines (I > 1), 0: adjacent points (I == 1)
+  unsigned magic_ns[12];   // ceil(2^32 / Ns) of stage s: j / Ns == __umulhi(j, magic) for j < 2^16
+  int TL, tpl_log2;        // lines per tile; threads per line = 2^tpl_log2
+  int line_fast;           // 1: adjacent threads load adjacent lines (I > 1), 0: adjacent points (I == 1)
   int swap_in, swap_out;
 };
+
+// compile-time cos / sin of 2 pi m / R (Taylor series about the nearest multiple of pi/2; |x| <= pi/4, 13 terms: < 1e-17)
+constexpr double ct_poly_cos(double x) {
+  double term = 1, sum = 1;
+  for (int i = 1; i <= 13; i++) { term *= -x * x / ((2 * i - 1) * (2 * i)); sum += term; }
+  return sum;
+}
+constexpr double ct_poly_sin(double x) {
+  double term = x, sum = x;
+  for (int i = 1; i <= 13; i++) { term *= -x * x / ((2 * i) * (2 * i + 1)); sum += term; }
+  return sum;
+}
+constexpr double ct_cos_turn(int m, int R) {   // cos(2 pi m / R), m in [0, R)
+  const double pi = 3.141592653589793238462643383279502884;
+  double x = 2 * pi * m / R;                                    // [0, 2 pi)
+  int quad = 0;
+  while (x > pi / 4) { x -= pi / 2; quad++; }
+  switch (quad & 3) {
+    case 0: return ct_poly_cos(x);
+    case 1: return -ct_poly_sin(x);
+    case 2: return -ct_poly_cos(x);
+    default: return ct_poly_sin(x);
+  }
+}
+constexpr double ct_sin_turn(int m, int R) { return ct_cos_turn((4 * m + 3 * R) % (4 * R), 4 * R); }   // sin(t) = cos(t - 1/4 turn)
+
+__device__ __forceinline__ int mpad(int i) { return i + (i >> 5); }   // one pad element per 32: de-phases the Stockham strides
 
 template <int R, typename C>
 __device__ __forceinline__ void small_dft(C* a) {
@@ -103,87 +131,126 @@ __device__ __forceinline__ void small_dft(C* a) {
     C r2 = C{-(s2 * d1.y - s1 * d2.y), s2 * d1.x - s1 * d2.x};   // i*(s2 d1 - s1 d2)
     a[0] = cadd(a[0], cadd(t1, t2));
     a[1] = cadd(m1, r1); a[4] = csub(m1, r1); a[2] = cadd(m2, r2); a[3] = csub(m2, r2);
+  } else if constexpr (R == 8 || R == 16) {
+    C v[R];
+    static_for<0, R>([&](auto ic) { constexpr int i = ic; v[i] = a[i]; });
+    dft<R>(v);                                             // cplx.cuh: radix-4 recursion, compile-time constants
+    static_for<0, R>([&](auto ic) { constexpr int i = ic; a[i] = v[i]; });
+  } else {
+    // odd primes 7, 11, 13: pairs (r, R-r) share cos / sin sums -- (R-1)^2 / 2 real multiplies, all compile-time roots
+    constexpr int H = (R - 1) / 2;
+    C t[H], d[H];
+    static_for<0, H>([&](auto ic) { constexpr int i = ic; t[i] = cadd(a[i + 1], a[R - 1 - i]); d[i] = csub(a[i + 1], a[R - 1 - i]); });
+    C sum = a[0];
+    static_for<0, H>([&](auto ic) { constexpr int i = ic; sum = cadd(sum, t[i]); });
+    static_for<1, H + 1>([&](auto qc) {
+      constexpr int q = qc;
+      T mx = a[0].x, my = a[0].y, rx = 0, ry = 0;
+      static_for<0, H>([&](auto ic) {
+        constexpr int i = ic;
+        constexpr int m = (q * (i + 1)) % R;
+        constexpr T c = (T)ct_cos_turn(m, R), sn = (T)(-ct_sin_turn(m, R));
+        mx += c * t[i].x; my += c * t[i].y;
+        rx -= sn * d[i].y; ry += sn * d[i].x;       // i * sn * d
+      });
+      a[q] = C{mx + rx, my + ry};
+      a[R - q] = C{mx - rx, my - ry};
+    });
+    a[0] = sum;
   }
 }
 
-// generic odd-prime DFT via the root table (R <= 13): O(R^2)
-template <typename C>
-__device__ __forceinline__ void prime_dft(C* a, int R, const C* __restrict__ tw, long long N) {
-  C y[13];
-  const long long step = N / R;  // w_R = w_N^(N/R)
-  for (int q = 0; q < R; q++) {
-    C acc = a[0];
-    for (int r = 1; r < R; r++) acc = cadd(acc, cmul(a[r], tw[(long long)((r * q) % R) * step]));
-    y[q] = acc;
+// one Stockham stage of radix R on this thread's line: butterflies j = tl, tl + TPL, ... < N/R
+template <int R, typename C>
+__device__ __forceinline__ void mixed_stage(const C* __restrict__ src, C* __restrict__ dst, const C* __restrict__ tw, int N, int Ns,
+                                            unsigned magic, int tl, int tpl) {
+  const int nb = N / R;
+  const int tmul = nb / Ns;                       // w_{Ns R}^{r k} = w_N^{r k N/(Ns R)}; r*k*tmul < N: no reduction needed
+  for (int j = tl; j < nb; j += tpl) {
+    const int jb = Ns > 1 ? (int)__umulhi((unsigned)j, magic) : j, k = j - jb * Ns;
+    C a[R];
+    static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r] = src[mpad(j + r * nb)]; });
+    if (Ns > 1) {
+      const int base = tmul * k;
+      static_for<1, R>([&](auto rc) { constexpr int r = rc; a[r] = cmul(a[r], __ldg(tw + base * r)); });
+    }
+    small_dft<R>(a);
+    const int o = jb * Ns * R + k;
+    static_for<0, R>([&](auto qc) { constexpr int q = qc; dst[mpad(o + q * Ns)] = a[q]; });
   }
-  for (int q = 0; q < R; q++) a[q] = y[q];
 }
 
 template <typename C>
-__global__ void mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw,
+__global__ void __launch_bounds__(sizeof(C) == 8 ? 512 : 256)
+mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw,
                                    real_of<C> scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = (int)p.N, TL = p.TL;
+  const int N = (int)p.N, TL = p.TL, tpl = 1 << p.tpl_log2;
+  const int pitch = mpad(N - 1) + 1;
   C* buf0 = reinterpret_cast<C*>(smem_raw);
-  C* buf1 = buf0 + (size_t)N * TL;
+  C* buf1 = buf0 + (size_t)pitch * TL;
   const long long nlines = p.O * p.I;
   const long long l0 = (long long)blockIdx.x * TL;
-  const int nthreads = blockDim.x, tid = threadIdx.x;
-  // load: smem layout [line][n]
-  for (int idx = tid; idx < N * TL; idx += nthreads) {
-    int l, n;
-    if (p.line_fast) { l = idx % TL; n = idx / TL; } else { n = idx % N; l = idx / N; }
+  const int tid = threadIdx.x;
+  // load.  Rows: thread group l streams its own line (adjacent threads = adjacent points).  Strided axes: adjacent
+  // threads = adjacent lines, the tile's TL lines give TL*sizeof(C) contiguous bytes per point index.
+  {
+    const int l = p.line_fast ? tid % TL : tid >> p.tpl_log2;
+    const int n0 = p.line_fast ? tid / TL : tid & (tpl - 1);
+    const int nstep = p.line_fast ? (int)blockDim.x / TL : tpl;
     const long long line = l0 + l;
-    C v = C{0, 0};
     if (line < nlines) {
-      const long long o = line / p.I, i = line % p.I;
-      v = in[o * p.N * p.I + (long long)n * p.I + i];
-      if (p.swap_in) v.y = -v.y;
+      const long long o = line / p.I, i = line - o * p.I;
+      const C* ip = in + o * p.N * p.I + i;
+      C* bp = buf0 + l * pitch;
+      for (int n = n0; n < N; n += nstep) {
+        C v = ip[(long long)n * p.I];
+        if (p.swap_in) v.y = -v.y;
+        bp[mpad(n)] = v;
+      }
     }
-    buf0[l * N + n] = v;
   }
   __syncthreads();
-  C* src = buf0;
-  C* dst = buf1;
+  const int l = tid >> p.tpl_log2, tl = tid & (tpl - 1);
+  C* src = buf0 + l * pitch;
+  C* dst = buf1 + l * pitch;
   int Ns = 1;
   for (int s = 0; s < p.nstages; s++) {
     const int R = p.radix[s];
-    const int nb = N / R;  // butterflies per line
-    for (int idx = tid; idx < nb * TL; idx += nthreads) {
-      const int l = idx / nb, j = idx % nb;
-      const int k = j % Ns;
-      C a[13];
-      const C* sp = src + l * N;
-      const long long tstep = (long long)(N / (Ns * R)) * k;  // w_{Ns R}^{r k} = w_N^{r k N/(Ns R)}
-      for (int r = 0; r < R; r++) {
-        C v = sp[j + r * nb];
-        if (r > 0 && k > 0) v = cmul(v, tw[(tstep * r) % N]);
-        a[r] = v;
-      }
+    if (l < TL) {
       switch (R) {
-        case 2: small_dft<2>(a); break;
-        case 3: small_dft<3>(a); break;
-        case 4: small_dft<4>(a); break;
-        case 5: small_dft<5>(a); break;
-        default: prime_dft(a, R, tw, p.N); break;
+        case 2: mixed_stage<2>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 3: mixed_stage<3>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 4: mixed_stage<4>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 5: mixed_stage<5>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 7: mixed_stage<7>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 8: mixed_stage<8>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 11: mixed_stage<11>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 13: mixed_stage<13>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        case 16: mixed_stage<16>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
+        default: break;
       }
-      C* dp = dst + l * N + (j / Ns) * Ns * R + k;
-      for (int q = 0; q < R; q++) dp[q * Ns] = a[q];
     }
     __syncthreads();
     C* t = src; src = dst; dst = t;
     Ns *= R;
   }
-  for (int idx = tid; idx < N * TL; idx += nthreads) {
-    int l, n;
-    if (p.line_fast) { l = idx % TL; n = idx / TL; } else { n = idx % N; l = idx / N; }
-    const long long line = l0 + l;
+  {
+    const C* res = (p.nstages & 1) ? buf1 : buf0;
+    const int ll = p.line_fast ? tid % TL : tid >> p.tpl_log2;
+    const int n0 = p.line_fast ? tid / TL : tid & (tpl - 1);
+    const int nstep = p.line_fast ? (int)blockDim.x / TL : tpl;
+    const long long line = l0 + ll;
     if (line < nlines) {
-      const long long o = line / p.I, i = line % p.I;
-      C v = src[l * N + n];
-      v.x *= scale; v.y *= scale;
-      if (p.swap_out) v.y = -v.y;
-      out[o * p.N * p.I + (long long)n * p.I + i] = v;
+      const long long o = line / p.I, i = line - o * p.I;
+      C* op = out + o * p.N * p.I + i;
+      const C* bp = res + ll * pitch;
+      const real_of<C> sy = p.swap_out ? -scale : scale;
+      for (int n = n0; n < N; n += nstep) {
+        C v = bp[mpad(n)];
+        v.x *= scale; v.y *= sy;
+        op[(long long)n * p.I] = v;
+      }
     }
   }
 }
@@ -194,13 +261,21 @@ __global__ void mixed_radix_kernel(const MixedParams p, const C* __restrict__ in
 static const size_t kMixedSmemCap = 160 * 1024;
 static const size_t kBluesteinWorkspaceCap = 512ull << 20;  // per buffer
 
+// radices in stage order: odd primes first (the first stage has no twiddles and an odd store stride), then the power of
+// two in as few stages as possible (16, 16, ..., then 8 / 4 / 8*4 instead of 16*2)
 static bool factor_small(long long n, std::vector<int>* f) {
   f->clear();
-  while (n % 4 == 0) { f->push_back(4); n /= 4; }
-  while (n % 2 == 0) { f->push_back(2); n /= 2; }
-  for (int pr : {3, 5, 7, 11, 13})
+  int a = 0;
+  while (n % 2 == 0) { a++; n /= 2; }
+  for (int pr : {13, 11, 7, 5, 3})
     while (n % pr == 0) { f->push_back(pr); n /= pr; }
-  return n == 1;
+  if (n != 1) return false;
+  while (a >= 5 || a == 4) { f->push_back(16); a -= 4; }
+  if (a == 1 && !f->empty() && f->back() == 16) { f->back() = 8; f->push_back(4); a = 0; }
+  if (a == 3) f->push_back(8);
+  else if (a == 2) f->push_back(4);
+  else if (a == 1) f->push_back(2);
+  return true;
 }
 
 template <typename T>
@@ -218,20 +293,26 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
   gp->O = O; gp->N = N; gp->I = I; gp->lines = O * I;
   std::vector<int> f;
   const bool smooth = factor_small(N, &f);
-  if (smooth && (size_t)N * esz * 2 <= kMixedSmemCap && f.size() <= 12) {
+  if (smooth && ((size_t)N + N / 32 + 1) * esz * 2 <= kMixedSmemCap && N < 65536 && f.size() <= 12) {
     gp->bluestein = 0;
     gp->nstages = (int)f.size();
-    // largest radices first: the stage with Ns == 1 has no twiddles
-    for (size_t i = 0; i < f.size(); i++) gp->radix[i] = f[f.size() - 1 - i];
-    int TL = (int)(kMixedSmemCap / ((size_t)N * esz * 2));
-    const int want = I > 1 ? 16 : 8;
+    for (size_t i = 0; i < f.size(); i++) gp->radix[i] = f[i];
+    // rows: ~64 KB of shared memory per CTA (3 CTAs per SM); strided axes: 8 lines (64-128 B runs) when they fit
+    const size_t line_bytes = ((size_t)N + N / 32 + 1) * esz * 2;
+    int TL = (int)((I > 1 ? kMixedSmemCap : (size_t)(64 * 1024)) / line_bytes);
+    const int want = I > 1 ? 8 : 4;
     if (TL > want) TL = want;
     if (TL < 1) TL = 1;
     if ((long long)TL > gp->lines) TL = (int)gp->lines;
     gp->TL = TL;
-    gp->smem = (size_t)N * TL * esz * 2;
-    long long work = (N / 2) * TL;
-    gp->threads = work >= 512 ? 512 : work >= 256 ? 256 : work >= 128 ? 128 : 64;
+    gp->smem = line_bytes * TL;
+    // threads per line: a power of two near N/16 (a radix-16 stage has N/16 butterflies), at most 1024 threads per CTA
+    int tl2 = 3;
+    while ((2 << tl2) <= N / 12 && tl2 < 8) tl2++;
+    while (((1 << tl2) * TL) > (is_double ? 256 : 512)) tl2--;
+    while (((1 << tl2) * TL) < 64) tl2++;
+    gp->tpl_log2 = tl2;
+    gp->threads = (1 << tl2) * TL;
     if (is_double) { std::vector<double> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(double)); }
     else { std::vector<float> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(float)); }
     if (!gp->tw) return B200FFT_ALLOC_FAILED;
@@ -306,7 +387,11 @@ static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst,
     MixedParams mp{};
     mp.O = gp.O; mp.N = gp.N; mp.I = gp.I; mp.nstages = gp.nstages;
     for (int i = 0; i < gp.nstages; i++) mp.radix[i] = gp.radix[i];
-    mp.TL = gp.TL; mp.line_fast = gp.I > 1;
+    mp.TL = gp.TL; mp.tpl_log2 = gp.tpl_log2; mp.line_fast = gp.I > 1;
+    {
+      long long Ns = 1;
+      for (int i = 0; i < gp.nstages; i++) { mp.magic_ns[i] = (unsigned)(((1ull << 32) + Ns - 1) / Ns); Ns *= gp.radix[i]; }
+    }
     mp.swap_in = mp.swap_out = 0;
     // the caller folds first/last-pass information into `inverse`: see launch_generic
     mp.swap_in = inverse & 1; mp.swap_out = (inverse >> 1) & 1;

@@ -26,7 +26,7 @@ struct GenericPass {
   int nstages = 0;
   int radix[40] = {0};
   void* tw = nullptr;             // device, N entries: exp(-2 pi i m/N)
-  int TL = 1, threads = 0;
+  int TL = 1, threads = 0, tpl_log2 = 0;
   size_t smem = 0;
   size_t workspace_bytes = 0;
   char desc[256] = {0};
