@@ -160,30 +160,61 @@ __device__ __forceinline__ void small_dft(C* a) {
   }
 }
 
-// one Stockham stage of radix R on this thread's line: butterflies j = tl, tl + TPL, ... < N/R
-template <int R, typename C>
-__device__ __forceinline__ void mixed_stage(const C* __restrict__ src, C* __restrict__ dst, const C* __restrict__ tw, int N, int Ns,
-                                            unsigned magic, int tl, int tpl) {
+// one Stockham stage of radix R on this thread's line: butterflies j = tl, tl + TPL, ... < N/R.
+// GIN: the first stage of a contiguous line reads global memory directly (unit stride across the threads of the line,
+// conjugating for the inverse); GOUT: the last stage writes global memory directly (scale, conjugate) -- two shared-memory
+// round trips and two barriers fewer per transform.
+template <int R, bool GIN, bool GOUT, typename C>
+__device__ __forceinline__ void mixed_stage(const C* __restrict__ src, C* __restrict__ dst, const C* __restrict__ gin, C* __restrict__ gout,
+                                            const C* __restrict__ tw, int N, int Ns, unsigned magic, int tl, int tpl, int swap_in,
+                                            int swap_out, real_of<C> scale) {
+  using T = real_of<C>;
   const int nb = N / R;
   const int tmul = nb / Ns;                       // w_{Ns R}^{r k} = w_N^{r k N/(Ns R)}; r*k*tmul < N: no reduction needed
   for (int j = tl; j < nb; j += tpl) {
     const int jb = Ns > 1 ? (int)__umulhi((unsigned)j, magic) : j, k = j - jb * Ns;
     C a[R];
-    static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r] = src[mpad(j + r * nb)]; });
+    if constexpr (GIN) {
+      static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r] = gin[j + r * nb]; });
+      if (swap_in) static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r].y = -a[r].y; });
+    } else {
+      static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r] = src[mpad(j + r * nb)]; });
+    }
     if (Ns > 1) {
       const int base = tmul * k;
       static_for<1, R>([&](auto rc) { constexpr int r = rc; a[r] = cmul(a[r], __ldg(tw + base * r)); });
     }
     small_dft<R>(a);
     const int o = jb * Ns * R + k;
-    static_for<0, R>([&](auto qc) { constexpr int q = qc; dst[mpad(o + q * Ns)] = a[q]; });
+    if constexpr (GOUT) {
+      const T sy = swap_out ? -scale : scale;
+      static_for<0, R>([&](auto qc) { constexpr int q = qc; gout[o + q * Ns] = C{a[q].x * scale, a[q].y * sy}; });
+    } else {
+      static_for<0, R>([&](auto qc) { constexpr int q = qc; dst[mpad(o + q * Ns)] = a[q]; });
+    }
+  }
+}
+
+template <bool GIN, bool GOUT, typename C>
+__device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, const C* gin, C* gout, const C* tw, int N, int Ns,
+                                                unsigned magic, int tl, int tpl, int swap_in, int swap_out, real_of<C> scale) {
+  switch (R) {
+    case 2: mixed_stage<2, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 3: mixed_stage<3, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 4: mixed_stage<4, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 5: mixed_stage<5, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 7: mixed_stage<7, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 8: mixed_stage<8, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 11: mixed_stage<11, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 13: mixed_stage<13, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    case 16: mixed_stage<16, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+    default: break;
   }
 }
 
 template <typename C>
 __global__ void __launch_bounds__(sizeof(C) == 8 ? 512 : 256)
-mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw,
-                                   real_of<C> scale) {
+mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw, real_of<C> scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = (int)p.N, TL = p.TL, tpl = 1 << p.tpl_log2;
   const int pitch = mpad(N - 1) + 1;
@@ -192,17 +223,41 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
   const long long nlines = p.O * p.I;
   const long long l0 = (long long)blockIdx.x * TL;
   const int tid = threadIdx.x;
-  // load.  Rows: thread group l streams its own line (adjacent threads = adjacent points).  Strided axes: adjacent
-  // threads = adjacent lines, the tile's TL lines give TL*sizeof(C) contiguous bytes per point index.
+  const int l = tid >> p.tpl_log2, tl = tid & (tpl - 1);     // compute mapping: one thread group per line
+
+  if (!p.line_fast) {
+    // contiguous lines: first stage straight from global memory, last stage straight to it
+    const bool live = l0 + l < nlines;      // (a dead group still meets the barriers)
+    const C* gin = in + (l0 + l) * p.N;
+    C* gout = out + (l0 + l) * p.N;
+    C* src = buf0 + l * pitch;
+    C* dst = buf1 + l * pitch;
+    int Ns = 1;
+    for (int s = 0; s < p.nstages; s++) {
+      const int R = p.radix[s];
+      const bool first = s == 0, last = s + 1 == p.nstages;
+      if (live) {
+        if (first && last) mixed_stage_any<true, true>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
+        else if (first) mixed_stage_any<true, false>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
+        else if (last) mixed_stage_any<false, true>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
+        else mixed_stage_any<false, false>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
+      }
+      if (!last) __syncthreads();
+      if (!first) { C* t = src; src = dst; dst = t; }   // the first stage wrote buf1 = `dst`; from then on ping-pong
+      else { src = buf1 + l * pitch; dst = buf0 + l * pitch; }
+      Ns *= R;
+    }
+    return;
+  }
+
+  // strided axis: adjacent threads = adjacent lines, the tile's TL lines give TL*sizeof(C) contiguous bytes per point
   {
-    const int l = p.line_fast ? tid % TL : tid >> p.tpl_log2;
-    const int n0 = p.line_fast ? tid / TL : tid & (tpl - 1);
-    const int nstep = p.line_fast ? (int)blockDim.x / TL : tpl;
-    const long long line = l0 + l;
+    const int ll = tid % TL, n0 = tid / TL, nstep = (int)blockDim.x / TL;
+    const long long line = l0 + ll;
     if (line < nlines) {
       const long long o = line / p.I, i = line - o * p.I;
       const C* ip = in + o * p.N * p.I + i;
-      C* bp = buf0 + l * pitch;
+      C* bp = buf0 + ll * pitch;
       for (int n = n0; n < N; n += nstep) {
         C v = ip[(long long)n * p.I];
         if (p.swap_in) v.y = -v.y;
@@ -211,35 +266,18 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
     }
   }
   __syncthreads();
-  const int l = tid >> p.tpl_log2, tl = tid & (tpl - 1);
   C* src = buf0 + l * pitch;
   C* dst = buf1 + l * pitch;
   int Ns = 1;
   for (int s = 0; s < p.nstages; s++) {
-    const int R = p.radix[s];
-    if (l < TL) {
-      switch (R) {
-        case 2: mixed_stage<2>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 3: mixed_stage<3>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 4: mixed_stage<4>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 5: mixed_stage<5>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 7: mixed_stage<7>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 8: mixed_stage<8>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 11: mixed_stage<11>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 13: mixed_stage<13>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        case 16: mixed_stage<16>(src, dst, tw, N, Ns, p.magic_ns[s], tl, tpl); break;
-        default: break;
-      }
-    }
+    mixed_stage_any<false, false>(p.radix[s], src, dst, (const C*)nullptr, (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl, 0, 0, scale);
     __syncthreads();
     C* t = src; src = dst; dst = t;
-    Ns *= R;
+    Ns *= p.radix[s];
   }
   {
     const C* res = (p.nstages & 1) ? buf1 : buf0;
-    const int ll = p.line_fast ? tid % TL : tid >> p.tpl_log2;
-    const int n0 = p.line_fast ? tid / TL : tid & (tpl - 1);
-    const int nstep = p.line_fast ? (int)blockDim.x / TL : tpl;
+    const int ll = tid % TL, n0 = tid / TL, nstep = (int)blockDim.x / TL;
     const long long line = l0 + ll;
     if (line < nlines) {
       const long long o = line / p.I, i = line - o * p.I;
