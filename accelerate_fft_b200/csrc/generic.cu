@@ -294,6 +294,74 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// lengths up to 32 that are not powers of two (3, 5, 6, 7, 9, ... 31, primes included): one THREAD per line, direct
+// O(N^2) sum from shared memory ([point][line] layout: conflict-free; root table broadcast).  A thread group per
+// 12-point line wasted most of the machine (11 % of HBM peak) and the primes 17..31 went through Bluestein.
+// ------------------------------------------------------------------------------------------
+struct TinyParams {
+  long long O, N, I, lines;
+  unsigned magic;          // ceil(2^20 / N)
+  int swap_in, swap_out;
+};
+
+template <typename C, int LPB>
+__global__ void __launch_bounds__(LPB) tiny_dft_kernel(const TinyParams p, const C* __restrict__ in, C* __restrict__ out,
+                                                       const C* __restrict__ tw, real_of<C> scale) {
+  using T = real_of<C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = (int)p.N, t = threadIdx.x;
+  C* xs = reinterpret_cast<C*>(smem_raw);          // [n][LPB]
+  C* ys = xs + (size_t)N * LPB;                     // [k][LPB]
+  C* ws = ys + (size_t)N * LPB;                     // [N] roots w_N^m
+  const long long l0 = (long long)blockIdx.x * LPB;
+  const int nl = (int)((p.lines - l0 < LPB) ? p.lines - l0 : LPB);
+  if (t < N) ws[t] = tw[t];
+  if (p.I == 1) {   // rows: the tile is one contiguous chunk of nl*N elements
+    const C* ip = in + l0 * N;
+    for (int idx = t; idx < nl * N; idx += LPB) {
+      const int line = (int)(((unsigned)idx * p.magic) >> 20), n = idx - line * N;
+      C v = ip[idx];
+      if (p.swap_in) v.y = -v.y;
+      xs[n * LPB + line] = v;
+    }
+  } else if (t < nl) {   // strided axis: adjacent threads = adjacent lines
+    const long long line = l0 + t, o = line / p.I, i = line - o * p.I;
+    const C* ip = in + o * p.N * p.I + i;
+    for (int n = 0; n < N; n++) {
+      C v = ip[(long long)n * p.I];
+      if (p.swap_in) v.y = -v.y;
+      xs[n * LPB + t] = v;
+    }
+  }
+  __syncthreads();
+  if (t < nl) {
+    const T sy = p.swap_out ? -scale : scale;
+    for (int k = 0; k < N; k++) {
+      C acc = xs[t];
+      int m = 0;
+      for (int n = 1; n < N; n++) {
+        m += k;
+        if (m >= N) m -= N;
+        acc = cadd(acc, cmul(xs[n * LPB + t], ws[m]));
+      }
+      ys[k * LPB + t] = C{acc.x * scale, acc.y * sy};
+    }
+  }
+  __syncthreads();
+  if (p.I == 1) {
+    C* op = out + l0 * N;
+    for (int idx = t; idx < nl * N; idx += LPB) {
+      const int line = (int)(((unsigned)idx * p.magic) >> 20), k = idx - line * N;
+      op[idx] = ys[k * LPB + line];
+    }
+  } else if (t < nl) {
+    const long long line = l0 + t, o = line / p.I, i = line - o * p.I;
+    C* op = out + o * p.N * p.I + i;
+    for (int k = 0; k < N; k++) op[(long long)k * p.I] = ys[k * LPB + t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static const size_t kMixedSmemCap = 160 * 1024;
@@ -329,6 +397,18 @@ static void fill_roots(std::vector<T>& v, long long N) {
 int plan_generic_axis(int is_double, long long O, long long N, long long I, GenericPass* gp, const Uploader& up) {
   const size_t esz = is_double ? 16 : 8;
   gp->O = O; gp->N = N; gp->I = I; gp->lines = O * I;
+  if (N <= 32) {   // (powers of two never get here)
+    gp->bluestein = 0;
+    gp->tiny = 1;
+    gp->threads = is_double ? 64 : 128;
+    gp->smem = ((size_t)2 * N * gp->threads + N) * esz;
+    if (is_double) { std::vector<double> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(double)); }
+    else { std::vector<float> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(float)); }
+    if (!gp->tw) return B200FFT_ALLOC_FAILED;
+    snprintf(gp->desc, sizeof gp->desc, "tiny direct N=%lld, one thread per line, %d lines per CTA smem=%zu (O=%lld I=%lld)", N, gp->threads,
+             gp->smem, O, I);
+    return 0;
+  }
   std::vector<int> f;
   const bool smooth = factor_small(N, &f);
   if (smooth && ((size_t)N + N / 32 + 1) * esz * 2 <= kMixedSmemCap && N < 65536 && f.size() <= 12) {
@@ -421,6 +501,17 @@ template <typename C>
 static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst, void* workspace, int inverse, double scale,
                                     cudaStream_t stream, long long* nl) {
   using T = real_of<C>;
+  if (gp.tiny) {
+    TinyParams tp{};
+    tp.O = gp.O; tp.N = gp.N; tp.I = gp.I; tp.lines = gp.lines;
+    tp.magic = (unsigned)(((1u << 20) + gp.N - 1) / gp.N);
+    tp.swap_in = inverse & 1; tp.swap_out = (inverse >> 1) & 1;
+    constexpr int LPB = sizeof(C) == 8 ? 128 : 64;
+    const long long tiles = (gp.lines + LPB - 1) / LPB;
+    tiny_dft_kernel<C, LPB><<<(unsigned)tiles, LPB, gp.smem, stream>>>(tp, src, dst, (const C*)gp.tw, (T)scale);
+    *nl += 1;
+    return cudaGetLastError();
+  }
   if (!gp.bluestein) {
     MixedParams mp{};
     mp.O = gp.O; mp.N = gp.N; mp.I = gp.I; mp.nstages = gp.nstages;
@@ -543,6 +634,8 @@ cudaError_t launch_centre(int is_double, const void* src, void* dst, long long d
 }
 
 int generic_set_attrs() {
+  cudaFuncSetAttribute(tiny_dft_kernel<float2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(tiny_dft_kernel<double2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   if (cudaFuncSetAttribute(mixed_radix_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;
   if (cudaFuncSetAttribute(mixed_radix_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)

@@ -14,6 +14,7 @@ namespace b200fft {
 
 struct GenericPass {
   int bluestein = 0;
+  int tiny = 0;                   // N <= 32, not a power of two: one thread per line, direct sum
   long long O = 1, N = 1, I = 1;  // array viewed as [O][N][I], transform along N
   long long lines = 0;            // O*I
   // Bluestein
