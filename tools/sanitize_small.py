@@ -34,6 +34,10 @@ for dt, n1 in ((np.complex64, 1024), (np.complex128, 512)):
 run("fft", (301, 8192), np.complex64, B200FFT_PIPE="1")           # pipe rows
 run("fft", (5, 1000), np.complex64); run("fft", (5, 1009), np.complex64)   # mixed radix, Bluestein
 for dt in (np.complex64, np.complex128):
+    for n in (3, 12, 17, 31):
+        run("fft", (300, n), dt); run("fft2D", (n, 70), dt)           # one thread per line, direct sum
+    run("fft", (9, 1536), dt); run("fft2D", (360, 50), dt); run("fft", (3, 9000), np.complex64)   # mixed radix rows / strided
+for dt in (np.complex64, np.complex128):
     for n in (2, 4, 8, 16, 32):
         run("fft", (1000, n), dt)                                 # rows staged through shared memory (ragged last tile)
     run("fft2D", (4096, 64), dt, B200FFT_CLUSTER_ROWS="0")
