@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -426,7 +427,11 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
     gp->smem = line_bytes * TL;
     // threads per line: a power of two near N/16 (a radix-16 stage has N/16 butterflies), at most 1024 threads per CTA
     int tl2 = 3;
-    while ((2 << tl2) <= N / 12 && tl2 < 8) tl2++;
+    {
+      const char* e = getenv("B200FFT_MIXED_TPL_DIV");
+      const int div = e && atoi(e) > 0 ? atoi(e) : 12;
+      while ((2 << tl2) <= N / div && tl2 < 9) tl2++;
+    }
     while (((1 << tl2) * TL) > (is_double ? 256 : 512)) tl2--;
     while (((1 << tl2) * TL) < 64) tl2++;
     gp->tpl_log2 = tl2;
