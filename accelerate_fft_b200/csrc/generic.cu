@@ -4,7 +4,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "../../include/b200fft.h"
@@ -83,12 +85,18 @@ struct MixedParams {
 // compile-time cos / sin of 2 pi m / R (Taylor series about the nearest multiple of pi/2; |x| <= pi/4, 13 terms: < 1e-17)
 constexpr double ct_poly_cos(double x) {
   double term = 1, sum = 1;
-  for (int i = 1; i <= 13; i++) { term *= -x * x / ((2 * i - 1) * (2 * i)); sum += term; }
+  for (int i = 1; i <= 13; i++) {
+    if (term < 1e-40 && term > -1e-40) break;   // (an underflow is not a constant expression)
+    term *= -x * x / ((2 * i - 1) * (2 * i)); sum += term;
+  }
   return sum;
 }
 constexpr double ct_poly_sin(double x) {
   double term = x, sum = x;
-  for (int i = 1; i <= 13; i++) { term *= -x * x / ((2 * i) * (2 * i + 1)); sum += term; }
+  for (int i = 1; i <= 13; i++) {
+    if (term < 1e-40 && term > -1e-40) break;
+    term *= -x * x / ((2 * i) * (2 * i + 1)); sum += term;
+  }
   return sum;
 }
 constexpr double ct_cos_turn(int m, int R) {   // cos(2 pi m / R), m in [0, R)
@@ -108,9 +116,58 @@ constexpr double ct_sin_turn(int m, int R) { return ct_cos_turn((4 * m + 3 * R) 
 __device__ __forceinline__ int mpad(int i) { return i + (i >> 5); }   // one pad element per 32: de-phases the Stockham strides
 
 template <int R, typename C>
+__device__ __forceinline__ void small_dft(C* a);
+
+// composite radix R = RA*RB inside one thread (n = RB*n1 + n2, k = k1 + RA*k2): RB transforms of RA points, the
+// twiddles w_R^(k1*n2) as compile-time constants, RA transforms of RB points -- two Stockham stages without the
+// shared-memory round trip between them
+template <int RA, int RB, typename C>
+__device__ __forceinline__ void comp_dft(C* a) {
+  using T = real_of<C>;
+  constexpr int R = RA * RB;
+  C y[R];
+  static_for<0, RB>([&](auto nc) {
+    constexpr int n2 = nc;
+    C t[RA];
+    static_for<0, RA>([&](auto ic) { constexpr int n1 = ic; t[n1] = a[RB * n1 + n2]; });
+    small_dft<RA>(t);
+    static_for<0, RA>([&](auto kc) {
+      constexpr int k1 = kc;
+      constexpr int m = (k1 * n2) % R;
+      if constexpr (m == 0) y[k1 * RB + n2] = t[k1];
+      else {
+        constexpr T c = (T)ct_cos_turn(m, R), sn = (T)(-ct_sin_turn(m, R));
+        y[k1 * RB + n2] = cmul(t[k1], C{c, sn});
+      }
+    });
+  });
+  static_for<0, RA>([&](auto kc) {
+    constexpr int k1 = kc;
+    C u[RB];
+    static_for<0, RB>([&](auto nc) { constexpr int n2 = nc; u[n2] = y[k1 * RB + n2]; });
+    small_dft<RB>(u);
+    static_for<0, RB>([&](auto qc) { constexpr int k2 = qc; a[k1 + RA * k2] = u[k2]; });
+  });
+}
+
+template <int R, typename C>
 __device__ __forceinline__ void small_dft(C* a) {
   using T = real_of<C>;
-  if constexpr (R == 2) {
+  if constexpr (R == 6) comp_dft<2, 3>(a);
+  else if constexpr (R == 9) comp_dft<3, 3>(a);
+  else if constexpr (R == 10) comp_dft<2, 5>(a);
+  else if constexpr (R == 12) comp_dft<4, 3>(a);
+  else if constexpr (R == 14) comp_dft<2, 7>(a);
+  else if constexpr (R == 15) comp_dft<3, 5>(a);
+  else if constexpr (R == 18) comp_dft<2, 9>(a);
+  else if constexpr (R == 20) comp_dft<4, 5>(a);
+  else if constexpr (R == 21) comp_dft<3, 7>(a);
+  else if constexpr (R == 24) comp_dft<8, 3>(a);
+  else if constexpr (R == 25) comp_dft<5, 5>(a);
+  else if constexpr (R == 27) comp_dft<3, 9>(a);
+  else if constexpr (R == 28) comp_dft<4, 7>(a);
+  else if constexpr (R == 30) comp_dft<5, 6>(a);
+  else if constexpr (R == 2) {
     C x = a[0], y = a[1];
     a[0] = cadd(x, y); a[1] = csub(x, y);
   } else if constexpr (R == 4) {
@@ -132,7 +189,7 @@ __device__ __forceinline__ void small_dft(C* a) {
     C r2 = C{-(s2 * d1.y - s1 * d2.y), s2 * d1.x - s1 * d2.x};   // i*(s2 d1 - s1 d2)
     a[0] = cadd(a[0], cadd(t1, t2));
     a[1] = cadd(m1, r1); a[4] = csub(m1, r1); a[2] = cadd(m2, r2); a[3] = csub(m2, r2);
-  } else if constexpr (R == 8 || R == 16) {
+  } else if constexpr (R == 8 || R == 16 || R == 32) {
     C v[R];
     static_for<0, R>([&](auto ic) { constexpr int i = ic; v[i] = a[i]; });
     dft<R>(v);                                             // cplx.cuh: radix-4 recursion, compile-time constants
@@ -162,20 +219,20 @@ __device__ __forceinline__ void small_dft(C* a) {
 }
 
 // one Stockham stage of radix R on this thread's line: butterflies j = tl, tl + TPL, ... < N/R.
-// GIN: the first stage of a contiguous line reads global memory directly (unit stride across the threads of the line,
-// conjugating for the inverse); GOUT: the last stage writes global memory directly (scale, conjugate) -- two shared-memory
-// round trips and two barriers fewer per transform.
-template <int R, bool GIN, bool GOUT, typename C>
-__device__ __forceinline__ void mixed_stage(const C* __restrict__ src, C* __restrict__ dst, const C* __restrict__ gin, C* __restrict__ gout,
-                                            const C* __restrict__ tw, int N, int Ns, unsigned magic, int tl, int tpl, int swap_in,
-                                            int swap_out, real_of<C> scale) {
+// gin != nullptr: the first stage of a contiguous line reads global memory directly (unit stride across the threads of
+// the line, conjugating for the inverse); gout != nullptr: the last stage writes global memory directly (scale,
+// conjugate) -- two shared-memory round trips and two barriers fewer per transform.
+template <int R, typename C>
+__device__ __noinline__ void mixed_stage(const C* __restrict__ src, C* __restrict__ dst, const C* __restrict__ gin, C* __restrict__ gout,
+                                         const C* __restrict__ tw, int N, int Ns, unsigned magic, int tl, int tpl, int swap_in,
+                                         int swap_out, real_of<C> scale) {
   using T = real_of<C>;
   const int nb = N / R;
   const int tmul = nb / Ns;                       // w_{Ns R}^{r k} = w_N^{r k N/(Ns R)}; r*k*tmul < N: no reduction needed
   for (int j = tl; j < nb; j += tpl) {
     const int jb = Ns > 1 ? (int)__umulhi((unsigned)j, magic) : j, k = j - jb * Ns;
     C a[R];
-    if constexpr (GIN) {
+    if (gin) {
       static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r] = gin[j + r * nb]; });
       if (swap_in) static_for<0, R>([&](auto rc) { constexpr int r = rc; a[r].y = -a[r].y; });
     } else {
@@ -187,7 +244,7 @@ __device__ __forceinline__ void mixed_stage(const C* __restrict__ src, C* __rest
     }
     small_dft<R>(a);
     const int o = jb * Ns * R + k;
-    if constexpr (GOUT) {
+    if (gout) {
       const T sy = swap_out ? -scale : scale;
       static_for<0, R>([&](auto qc) { constexpr int q = qc; gout[o + q * Ns] = C{a[q].x * scale, a[q].y * sy}; });
     } else {
@@ -196,21 +253,25 @@ __device__ __forceinline__ void mixed_stage(const C* __restrict__ src, C* __rest
   }
 }
 
-template <bool GIN, bool GOUT, typename C>
+template <typename C>
 __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, const C* gin, C* gout, const C* tw, int N, int Ns,
                                                 unsigned magic, int tl, int tpl, int swap_in, int swap_out, real_of<C> scale) {
-  switch (R) {
-    case 2: mixed_stage<2, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 3: mixed_stage<3, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 4: mixed_stage<4, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 5: mixed_stage<5, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 7: mixed_stage<7, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 8: mixed_stage<8, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 11: mixed_stage<11, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 13: mixed_stage<13, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    case 16: mixed_stage<16, GIN, GOUT>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
-    default: break;
+#define MS_CASE(r) case r: mixed_stage<r>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
+  if constexpr (sizeof(C) == 8) {
+    switch (R) {
+      MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6) MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12) MS_CASE(13)
+      MS_CASE(14) MS_CASE(15) MS_CASE(16) MS_CASE(18) MS_CASE(20) MS_CASE(21) MS_CASE(24) MS_CASE(25) MS_CASE(27) MS_CASE(28) MS_CASE(30)
+      MS_CASE(32)
+      default: break;
+    }
+  } else {   // c128: at most 16 values per thread
+    switch (R) {
+      MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6) MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12) MS_CASE(13)
+      MS_CASE(14) MS_CASE(15) MS_CASE(16)
+      default: break;
+    }
   }
+#undef MS_CASE
 }
 
 template <typename C>
@@ -238,10 +299,8 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
       const int R = p.radix[s];
       const bool first = s == 0, last = s + 1 == p.nstages;
       if (live) {
-        if (first && last) mixed_stage_any<true, true>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
-        else if (first) mixed_stage_any<true, false>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
-        else if (last) mixed_stage_any<false, true>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
-        else mixed_stage_any<false, false>(R, src, dst, gin, gout, tw, N, Ns, p.magic_ns[s], tl, tpl, p.swap_in, p.swap_out, scale);
+        mixed_stage_any(R, (const C*)src, dst, first ? gin : (const C*)nullptr, last ? gout : (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl,
+                        p.swap_in, p.swap_out, scale);
       }
       if (!last) __syncthreads();
       if (!first) { C* t = src; src = dst; dst = t; }   // the first stage wrote buf1 = `dst`; from then on ping-pong
@@ -271,7 +330,7 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
   C* dst = buf1 + l * pitch;
   int Ns = 1;
   for (int s = 0; s < p.nstages; s++) {
-    mixed_stage_any<false, false>(p.radix[s], src, dst, (const C*)nullptr, (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl, 0, 0, scale);
+    mixed_stage_any(p.radix[s], (const C*)src, dst, (const C*)nullptr, (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl, 0, 0, scale);
     __syncthreads();
     C* t = src; src = dst; dst = t;
     Ns *= p.radix[s];
@@ -368,20 +427,38 @@ __global__ void __launch_bounds__(LPB) tiny_dft_kernel(const TinyParams p, const
 static const size_t kMixedSmemCap = 160 * 1024;
 static const size_t kBluesteinWorkspaceCap = 512ull << 20;  // per buffer
 
-// radices in stage order: odd primes first (the first stage has no twiddles and an odd store stride), then the power of
-// two in as few stages as possible (16, 16, ..., then 8 / 4 / 8*4 instead of 16*2)
-static bool factor_small(long long n, std::vector<int>* f) {
+// Fewest Stockham stages over the radices a thread can hold (c64: up to 32 values, c128: up to 16); among equal counts
+// the most balanced product; odd radices first (the first stage has no twiddles and an odd store stride).
+static bool factor_small(long long n, std::vector<int>* f, int rmax) {
+  static const int kRad[] = {32, 30, 28, 27, 25, 24, 21, 20, 18, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
   f->clear();
-  int a = 0;
-  while (n % 2 == 0) { a++; n /= 2; }
-  for (int pr : {13, 11, 7, 5, 3})
-    while (n % pr == 0) { f->push_back(pr); n /= pr; }
-  if (n != 1) return false;
-  while (a >= 5 || a == 4) { f->push_back(16); a -= 4; }
-  if (a == 1 && !f->empty() && f->back() == 16) { f->back() = 8; f->push_back(4); a = 0; }
-  if (a == 3) f->push_back(8);
-  else if (a == 2) f->push_back(4);
-  else if (a == 1) f->push_back(2);
+  {
+    long long m = n;
+    for (int pr : {2, 3, 5, 7, 11, 13}) while (m % pr == 0) m /= pr;
+    if (m != 1) return false;
+  }
+  if (n >= (1LL << 20)) return false;
+  // best[m] = (stages, largest radix, first radix): fewest stages, then the smallest largest radix (balanced stages
+  // keep the butterflies per line high and the registers per thread low)
+  struct Best { int stages, maxrad, rad; };
+  std::vector<Best> memo((size_t)n + 1, Best{-1, 0, 0});
+  std::function<Best(long long)> go = [&](long long m) -> Best {
+    if (m == 1) return Best{0, 0, 0};
+    if (memo[(size_t)m].stages >= 0) return memo[(size_t)m];
+    Best best{1 << 20, 1 << 20, 0};
+    for (int r : kRad) {
+      if (r > rmax || m % r) continue;
+      const Best c = go(m / r);
+      if (c.stages >= (1 << 20)) continue;
+      const int st = c.stages + 1, mx = c.maxrad > r ? c.maxrad : r;
+      if (st < best.stages || (st == best.stages && mx < best.maxrad)) best = Best{st, mx, r};
+    }
+    memo[(size_t)m] = best;
+    return best;
+  };
+  if (go(n).stages >= (1 << 20)) return false;
+  for (long long m = n; m > 1; m /= memo[(size_t)m].rad) f->push_back(memo[(size_t)m].rad);
+  std::stable_sort(f->begin(), f->end(), [](int a, int b) { return (a & 1) > (b & 1); });   // odd radices first
   return true;
 }
 
@@ -411,31 +488,33 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
     return 0;
   }
   std::vector<int> f;
-  const bool smooth = factor_small(N, &f);
+  const bool smooth = N < (1LL << 20) && factor_small(N, &f, is_double ? 16 : 32);
   if (smooth && ((size_t)N + N / 32 + 1) * esz * 2 <= kMixedSmemCap && N < 65536 && f.size() <= 12) {
     gp->bluestein = 0;
     gp->nstages = (int)f.size();
     for (size_t i = 0; i < f.size(); i++) gp->radix[i] = f[i];
-    // rows: ~64 KB of shared memory per CTA (3 CTAs per SM); strided axes: 8 lines (64-128 B runs) when they fit
+    // threads per line: the largest power of two not above the butterflies per line of the widest stage (so that no
+    // stage leaves most of a line's threads idle); lines per CTA: enough for >= 128 threads, within ~64 KB of shared
+    // memory for rows (3 CTAs per SM) and 8 lines (64-128 B runs) for strided axes
     const size_t line_bytes = ((size_t)N + N / 32 + 1) * esz * 2;
+    int rbig = 2;
+    for (int r : f) rbig = r > rbig ? r : rbig;
+    int tl2 = 0;
+    while ((2 << tl2) <= N / rbig && tl2 < 8) tl2++;
+    const int tmax = is_double ? 256 : 512;
+    int want = I > 1 ? 8 : 4;
+    while ((want << tl2) < 64) want *= 2;
     int TL = (int)((I > 1 ? kMixedSmemCap : (size_t)(64 * 1024)) / line_bytes);
-    const int want = I > 1 ? 8 : 4;
     if (TL > want) TL = want;
     if (TL < 1) TL = 1;
     if ((long long)TL > gp->lines) TL = (int)gp->lines;
+    while ((TL << tl2) > tmax && tl2 > 0) tl2--;
+    while ((TL << tl2) > tmax && TL > 1) TL--;
+    while ((TL << tl2) < 32) tl2++;
     gp->TL = TL;
     gp->smem = line_bytes * TL;
-    // threads per line: a power of two near N/16 (a radix-16 stage has N/16 butterflies), at most 1024 threads per CTA
-    int tl2 = 3;
-    {
-      const char* e = getenv("B200FFT_MIXED_TPL_DIV");
-      const int div = e && atoi(e) > 0 ? atoi(e) : 12;
-      while ((2 << tl2) <= N / div && tl2 < 9) tl2++;
-    }
-    while (((1 << tl2) * TL) > (is_double ? 256 : 512)) tl2--;
-    while (((1 << tl2) * TL) < 64) tl2++;
     gp->tpl_log2 = tl2;
-    gp->threads = (1 << tl2) * TL;
+    gp->threads = TL << tl2;
     if (is_double) { std::vector<double> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(double)); }
     else { std::vector<float> h(2 * (size_t)N); fill_roots(h, N); gp->tw = up(h.data(), h.size() * sizeof(float)); }
     if (!gp->tw) return B200FFT_ALLOC_FAILED;
