@@ -1117,6 +1117,7 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
     const double sc = last ? scale : 1.0;
     cudaError_t ce = cudaSuccess;
     const bool rotate = shifted && ps.axis_last;
+    bool pipe_done = false;
     if (!rotate && ps.pipe && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
       Geom g = ps.g;
       g.swap_in = inverse && first;
@@ -1135,8 +1136,15 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = (unsigned)ps.pipe->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = ps.pipe->CS > 1 ? 1 : 0;
-      ce = cudaLaunchKernelExC(&cfg, ps.pipe->func, args);
-      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (cudaLaunchKernelExC(&cfg, ps.pipe->func, args) == cudaSuccess) {
+        pipe_done = true;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      } else {
+        cudaGetLastError();   // e.g. cluster launches refused under a partitioned device: the lock-step kernel serves the pass
+      }
+    }
+    if (pipe_done) {
+      // the pass is on its way
     } else if (ps.kind == PK_LINES) {
       Geom g = ps.g;
       g.swap_in = inverse && first;
