@@ -50,7 +50,8 @@ def _prep(arr):
     if not arr.is_cuda:
         raise RuntimeError("accelerate_fft_b200 runs on the GPU only; got a %s tensor (no CPU fallback)" % arr.device)
     typ = _type_of(arr)
-    arr = arr.contiguous()
+    # lazy conj / neg views share storage with the un-conjugated tensor: materialise them, the C ABI sees raw memory
+    arr = arr.resolve_conj().resolve_neg().contiguous()
     out = torch.empty_like(arr)
     stream = torch.cuda.current_stream(arr.device).cuda_stream
     return arr, out, typ, ctypes.c_void_p(stream)
@@ -207,7 +208,7 @@ def run_host_seq(kind, modes, h_in, h_out=None):
         torch = _torch()
         if h_in.is_cuda:
             raise RuntimeError("run_host_seq takes host arrays")
-        h_in = h_in.contiguous()
+        h_in = h_in.resolve_conj().resolve_neg().contiguous()
         if h_out is None:
             h_out = torch.empty_like(h_in)
         typ = _type_of(h_in)

@@ -4,6 +4,7 @@
 // generic_kernel.cu) = one HBM read + one HBM write of the whole array.  Exec enqueues the passes on
 // the caller's stream; scratch is stream-ordered (cudaMallocAsync) so concurrent execs of one plan
 // on different streams do not share state (cf. PTX/Plans.hs:86 -- exec runs outside the cache lock).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -21,6 +22,7 @@
 #include "registry.h"
 #include "fft_kernel.cuh"
 #include "fused_kernel.cuh"
+#include "band_kernel.cuh"
 
 namespace b200fft {
 
@@ -43,6 +45,11 @@ static std::vector<FusedEntry>& freg() {
   return r;
 }
 static void add_fused(const FusedEntry& e) { freg().push_back(e); }
+static std::vector<BandEntry>& breg() {
+  static std::vector<BandEntry> r;
+  return r;
+}
+static void add_band(const BandEntry& e) { breg().push_back(e); }
 static std::once_flag g_reg_once;
 static void ensure_registry() {
   std::call_once(g_reg_once, [] {
@@ -57,6 +64,7 @@ static void ensure_registry() {
     register_cluster(add_entry);
     register_pipe(add_entry);
     register_fused(add_fused);
+    register_band(add_band);
   });
 }
 
@@ -106,6 +114,12 @@ const FusedEntry* find_fused(int is_double, int NA, int flavA, int twA, int NB, 
       return &e;
   return nullptr;
 }
+const BandEntry* find_band(int is_double, int mode, int outer, int N1, int N2) {
+  ensure_registry();
+  for (const auto& e : breg())
+    if (e.is_double == is_double && e.mode == mode && e.outer == outer && e.N1 == N1 && e.N2 == N2) return &e;
+  return nullptr;
+}
 int list_kernels(const KernelEntry** out, int max) {
   ensure_registry();
   int n = 0;
@@ -151,7 +165,7 @@ cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t s) { return scratch_
 // ------------------------------------------------------------------------------------------
 enum Buf { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3, PK_FUSED2 = 4, PK_CLUSTER = 5 };
+enum PassKind { PK_LINES = 0, PK_GENERIC = 1, PK_BLUESTEIN = 2, PK_COPY = 3, PK_FUSED2 = 4, PK_CLUSTER = 5, PK_BAND = 6 };
 
 struct Pass {
   int kind = PK_LINES;
@@ -179,6 +193,15 @@ struct Pass {
   bool mid_in_dst = false;         // PK_FUSED2: phase A writes into dst (in place there) instead of scratch slots
   int fused_grid = 0;              // PK_FUSED2: persistent CTAs
   bool first_swap_a = true;
+  // PK_BAND: two phases fused through L2 (band_kernel.cuh); tws / twsB = stage twiddles, tw_lo / tw_hi = inner four-step table
+  const BandEntry* bz = nullptr;
+  BandParams bp{};
+  void* otw_lo = nullptr;          // outer four-step table (OUTER kernels)
+  void* otw_hi = nullptr;
+  unsigned long long tm_dims[4] = {1, 1, 1, 1};     // tensor map of phase A's input: extents (elements of the real type) ...
+  unsigned long long tm_strides[3] = {0, 0, 0};     // ... byte strides of dims 1..3 ...
+  unsigned tm_box[4] = {1, 1, 1, 1};                // ... and the box of one tile
+  int band_grid = 0;
   std::string desc;
 };
 
@@ -199,6 +222,9 @@ struct b200fft_plan_s {
   size_t extra_bytes = 0;     // bluestein workspace
   size_t band_bytes = 0;      // fused passes: two L2-resident band slots + the ticket / progress counters
   bool no_shift = false;      // built by a whole-transform builder that does not mark the axes' last passes (b200fftExecShifted)
+  // Plans holding a PK_BAND pass need 16-byte aligned buffers (TMA) and cannot rotate their stores: the same transform
+  // planned without band passes serves misaligned buffers and b200fftExecShifted.
+  b200fft_plan_s* fallback = nullptr;
 };
 
 namespace b200fft {
@@ -614,6 +640,69 @@ struct Builder {
     return fused_pass(fz, ga, gb, fp, 0, true, true, "plane-xy");
   }
 
+  // ---- two four-step phases in one persistent TMA-fed launch, intermediate in L2 (band_kernel.cuh) ------------
+  bool no_band = false;
+  // strided axis [O][N][I], N = N1*N2: bands of Wb adjacent columns, in place at band granularity
+  bool try_band_strided(long long O, long long N, long long I, bool outer, long long outer_L, long long outer_col0) {
+    if (no_band || (getenv("B200FFT_BAND") && atoi(getenv("B200FFT_BAND")) == 0)) return false;
+    const BandEntry* bz = nullptr;
+    long long N1 = 0, N2 = 0;
+    for (long long n1 : {64LL, 128LL, 256LL, 32LL}) {
+      if (N % n1) continue;
+      bz = find_band(p->is_double, MODE_STRIDED, outer ? 1 : 0, (int)n1, (int)(N / n1));
+      if (bz) { N1 = n1; N2 = N / n1; break; }
+    }
+    if (!bz) return false;
+    const long long esz = (long long)esize(p);
+    long long Wb = env_int("B200FFT_BAND_COLS", bz->TLA > bz->TLB ? bz->TLA : bz->TLB);
+    if (Wb % bz->TLA || Wb % bz->TLB || I % Wb) return false;
+    // TMA: 16-byte aligned strides, extents below 2^32, byte strides below 2^40
+    if ((I * esz) % 16 || 2 * I >= (1LL << 32) || N * I * esz >= (1LL << 40) || O >= (1LL << 31)) return false;
+    const long long nbi = I / Wb, nbands = O * nbi;
+    const long long nA = N2 * (Wb / bz->TLA), nB = N1 * (Wb / bz->TLB);
+    if (nbands >= (1LL << 24) || nbands * (nA + nB) >= (1LL << 31)) return false;
+    if (nbands * (nA + nB) < 4 * 148) return false;              // too little work for a persistent launch
+    if ((N1 * bz->b.N / bz->b.E) * I * esz >= (1LL << 32)) return false;   // 32-bit byte step between a thread's stores
+    Pass ps;
+    ps.kind = PK_BAND;
+    ps.bz = bz;
+    BandParams bp{};
+    bp.nbands = (int)nbands; bp.nA = (int)nA; bp.nB = (int)nB;
+    bp.la = env_int("B200FFT_BAND_LA", 6);
+    if (bp.la > bp.nbands) bp.la = bp.nbands;
+    bp.nslots = env_int("B200FFT_BAND_SLOTS", bp.la + 4);
+    if (bp.nslots < bp.la + 1) bp.nslots = bp.la + 1;
+    bp.nbi = (int)nbi;
+    bp.a_ncg = (int)(Wb / bz->TLA);
+    bp.slot_elems = N * Wb;
+    bp.out_bo = N * I; bp.out_bi = Wb; bp.out_ks = I;
+    bp.wb = (int)Wb;
+    ps.tws = make_stage_twiddles(p, &bz->a);
+    ps.twsB = make_stage_twiddles(p, &bz->b);
+    make_fourstep_tables(p, N, &bp.tw_lo_bits, &ps.tw_lo, &ps.tw_hi);
+    if (outer) {
+      make_fourstep_tables(p, outer_L, &bp.otw_lo_bits, &ps.otw_lo, &ps.otw_hi);
+      bp.otw_col0 = outer_col0;
+    }
+    ps.bp = bp;
+    ps.tm_dims[0] = 2ull * (unsigned long long)I; ps.tm_dims[1] = (unsigned long long)N2; ps.tm_dims[2] = (unsigned long long)N1; ps.tm_dims[3] = (unsigned long long)O;
+    ps.tm_strides[0] = (unsigned long long)(I * esz); ps.tm_strides[1] = (unsigned long long)(N2 * I * esz); ps.tm_strides[2] = (unsigned long long)(N * I * esz);
+    ps.tm_box[0] = 2u * (unsigned)bz->TLA; ps.tm_box[1] = 1; ps.tm_box[2] = (unsigned)N1; ps.tm_box[3] = 1;
+    ps.inplace_ok = true;
+    ps.ntiles = nbands * (nA + nB);
+    const size_t need = counters_bytes(bp.nbands) + (size_t)bp.nslots * (size_t)bp.slot_elems * esize(p);
+    if (need > p->band_bytes) p->band_bytes = need;
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "4step-strided: band A[N=%d col+tw TL=%d] -> L2 slots -> B[N=%d col%s TL=%d] | persistent TMA-fed, threads=%d smem=%zu bands=%lld x %lld cols "
+             "tiles/band=%lld+%lld slot=%.1f MiB x%d lookahead=%d",
+             bz->N1, bz->TLA, bz->N2, outer ? "+outer tw" : "", bz->TLB, bz->threads, bz->smem, nbands, Wb, nA, nB,
+             (double)bp.slot_elems * esize(p) / 1048576.0, bp.nslots, bp.la);
+    ps.desc = buf;
+    push(ps);
+    return true;
+  }
+
   // longest strided axis done in one pass (>= 64 B runs)
   int max_col_n() const { return env_int("B200FFT_MAX_COL_N", 2048); }
   int max_row_n() const { return p->is_double ? 8192 : 16384; }  // largest N with a row kernel
@@ -665,6 +754,7 @@ struct Builder {
 
   // four-step along a strided axis: [O][N][I], N = N1*N2, n = n1*N2 + n2, k = k1 + N1*k2
   void fourstep_strided(long long O, long long N, long long I) {
+    if (try_band_strided(O, N, I, false, 0, 0)) return;
     if (try_fused_strided(O, N, I)) return;
     long long N1, N2;
     // small sub-lengths keep the [N][TL] tiles small; cap at 1024 so TL stays >= 8
@@ -960,6 +1050,15 @@ static int set_func_attrs(b200fft_plan_s* p) {
       long long grid = (long long)nsm * occ;
       ps.fused_grid = (int)(grid < ps.ntiles ? grid : ps.ntiles);
     }
+    if (ps.kind == PK_BAND) {
+      int dev = 0, nsm = 0, occ = 0;
+      if (cudaFuncSetAttribute(ps.bz->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.bz->smem) != cudaSuccess ||
+          cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.bz->func, ps.bz->threads, ps.bz->smem) != cudaSuccess || occ < 1)
+        return B200FFT_INTERNAL_ERROR;
+      const long long grid = (long long)nsm * occ;
+      ps.band_grid = (int)(grid < ps.ntiles ? grid : ps.ntiles);
+    }
     if (ps.kind == PK_LINES && ps.ring) {
       int dev = 0, nsm = 0, occ = 0;
       bool ok = cudaFuncSetAttribute(ps.ring->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.ring->smem) == cudaSuccess &&
@@ -988,6 +1087,31 @@ static int finish_plan(b200fft_plan_s* p, Builder& b, b200fftHandle* out) {
   return B200FFT_SUCCESS;
 }
 
+// Create a plan with `init` (fills type / rank / extents) and `build` (pushes the passes); when the result holds a
+// band pass, the same transform is planned again without band passes as its fallback (see b200fft_plan_s::fallback).
+template <class Init, class Build>
+static int create_plan(b200fftHandle* out, Init&& init, Build&& build) {
+  auto mk = [&](bool no_band, b200fftHandle* h) {
+    auto* p = new b200fft_plan_s;
+    init(p);
+    Builder b{p};
+    b.no_band = no_band;
+    build(b);
+    return finish_plan(p, b, h);
+  };
+  b200fftHandle h = nullptr;
+  if (int e = mk(false, &h)) return e;
+  bool has_band = false;
+  for (const auto& ps : h->passes) has_band |= ps.kind == PK_BAND;
+  if (has_band) {
+    b200fftHandle fb = nullptr;
+    if (int e = mk(true, &fb)) { b200fftDestroy(h); return e; }
+    h->fallback = fb;
+  }
+  *out = h;
+  return B200FFT_SUCCESS;
+}
+
 static int check_type(int type, int* is_double) {
   if (type == B200FFT_C2C) { *is_double = 0; return 0; }
   if (type == B200FFT_Z2Z) { *is_double = 1; return 0; }
@@ -1013,11 +1137,8 @@ int b200fftPlanMany1d(b200fftHandle* plan, int64_t n, int64_t batch, int type) {
   if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
   if (n < 1 || batch < 1) return B200FFT_INVALID_SIZE;
   if (int e = have_device()) return e;
-  auto* p = new b200fft_plan_s;
-  p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = batch; p->total = n * batch;
-  Builder b{p};
-  b.axis(batch, n, 1);
-  return finish_plan(p, b, plan);
+  return create_plan(plan, [&](b200fft_plan_s* p) { p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = batch; p->total = n * batch; },
+                     [&](Builder& b) { b.axis(batch, n, 1); });
 }
 
 int b200fftPlanAxis(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner, int type) {
@@ -1026,11 +1147,8 @@ int b200fftPlanAxis(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner
   if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
   if (n < 1 || outer < 1 || inner < 1) return B200FFT_INVALID_SIZE;
   if (int e = have_device()) return e;
-  auto* p = new b200fft_plan_s;
-  p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = outer * inner; p->total = n * outer * inner;
-  Builder b{p};
-  b.axis(outer, n, inner);
-  return finish_plan(p, b, plan);
+  return create_plan(plan, [&](b200fft_plan_s* p) { p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = outer * inner; p->total = n * outer * inner; },
+                     [&](Builder& b) { b.axis(outer, n, inner); });
 }
 
 int b200fftPlan1d(b200fftHandle* plan, int64_t n, int type, int64_t batch) { return b200fftPlanMany1d(plan, n, batch, type); }
@@ -1041,14 +1159,13 @@ int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type) {
   if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
   if (h < 1 || w < 1) return B200FFT_INVALID_SIZE;
   if (int e = have_device()) return e;
-  auto* p = new b200fft_plan_s;
-  p->is_double = dbl; p->rank = 2; p->dims[0] = h; p->dims[1] = w; p->total = h * w;
-  Builder b{p};
-  if (!b.try_cluster_rows_2d(h, w) && !b.try_pair_2d(h, w)) {
-    b.axis(h, w, 1);   // rows
-    b.axis(1, h, w);   // columns
-  }
-  return finish_plan(p, b, plan);
+  return create_plan(plan, [&](b200fft_plan_s* p) { p->is_double = dbl; p->rank = 2; p->dims[0] = h; p->dims[1] = w; p->total = h * w; },
+                     [&](Builder& b) {
+                       if (!b.try_cluster_rows_2d(h, w) && !b.try_pair_2d(h, w)) {
+                         b.axis(h, w, 1);   // rows
+                         b.axis(1, h, w);   // columns
+                       }
+                     });
 }
 
 int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type) {
@@ -1057,18 +1174,34 @@ int b200fftPlan3d(b200fftHandle* plan, int64_t d, int64_t h, int64_t w, int type
   if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
   if (d < 1 || h < 1 || w < 1) return B200FFT_INVALID_SIZE;
   if (int e = have_device()) return e;
-  auto* p = new b200fft_plan_s;
-  p->is_double = dbl; p->rank = 3; p->dims[0] = d; p->dims[1] = h; p->dims[2] = w; p->total = d * h * w;
-  Builder b{p};
-  if (!b.try_fused_plane(d, h, w)) {
-    b.axis(d * h, w, 1);   // x
-    b.axis(d, h, w);       // y
-  }
-  b.axis(1, d, h * w);   // z
-  return finish_plan(p, b, plan);
+  return create_plan(plan, [&](b200fft_plan_s* p) { p->is_double = dbl; p->rank = 3; p->dims[0] = d; p->dims[1] = h; p->dims[2] = w; p->total = d * h * w; },
+                     [&](Builder& b) {
+                       if (!b.try_fused_plane(d, h, w)) {
+                         b.axis(d * h, w, 1);   // x
+                         b.axis(d, h, w);       // y
+                       }
+                       b.axis(1, d, h * w);   // z
+                     });
 }
 
 static int exec_common(b200fftHandle p, const void* in, void* out, int direction, double scale, bool shifted, b200fftStream stream_);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda.so
+typedef CUresult (*tensor_map_encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_t tensor_map_encoder() {
+  static tensor_map_encode_t fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return (tensor_map_encode_t)f;
+  }();
+  return fn;
+}
 
 int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
   return exec_common(p, in, out, direction, scale, false, stream_);
@@ -1080,6 +1213,7 @@ int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction,
 // (odd / non-power-of-two extents): the caller then runs the stand-alone shift (accfft_fft_centred does).
 int b200fftExecShifted(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
+  if (p->fallback) return b200fftExecShifted(p->fallback, in, out, direction, scale, stream_);
   if (p->no_shift) return B200FFT_NOT_SUPPORTED;
   for (const Pass& ps : p->passes)
     if (ps.axis_last && (ps.kind != PK_LINES || ps.k->N < 2 || (ps.k->N & 1))) return B200FFT_NOT_SUPPORTED;
@@ -1090,6 +1224,8 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
   if (!in || !out || in == out) return B200FFT_INVALID_VALUE;
   if (direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) return B200FFT_INVALID_VALUE;
+  if (p->fallback && ((((uintptr_t)in | (uintptr_t)out) & 15) != 0 || !tensor_map_encoder()))
+    return exec_common(p->fallback, in, out, direction, scale, shifted, stream_);
   cudaStream_t stream = (cudaStream_t)stream_;
   void* scratch = nullptr;
   void* extra = nullptr;
@@ -1201,6 +1337,30 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
       if (ce == cudaSuccess)
         ce = cudaLaunchCooperativeKernel(ps.fz->func, dim3((unsigned)ps.fused_grid), dim3(ps.fz->threads), args, ps.fz->smem, stream);
       g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (ps.kind == PK_BAND) {
+      BandParams bp = ps.bp;
+      bp.swap_in = inverse && first;
+      bp.swap_out = inverse && last;
+      const size_t cb = Builder::counters_bytes(bp.nbands);
+      unsigned* counters = (unsigned*)band;
+      void* slots = (void*)((char*)band + cb);
+      alignas(64) CUtensorMap tm;
+      cuuint64_t dims[4] = {ps.tm_dims[0], ps.tm_dims[1], ps.tm_dims[2], ps.tm_dims[3]};
+      cuuint64_t strides[3] = {ps.tm_strides[0], ps.tm_strides[1], ps.tm_strides[2]};
+      cuuint32_t box[4] = {ps.tm_box[0], ps.tm_box[1], ps.tm_box[2], ps.tm_box[3]};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUresult cr = tensor_map_encoder()(&tm, p->is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                               const_cast<void*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) { status = B200FFT_EXEC_FAILED; break; }
+      ce = cudaMemsetAsync(counters, 0, cb, stream);
+      float scf = (float)sc;
+      double scd = sc;
+      void* args[] = {(void*)&tm, (void*)&bp, (void*)&dst, (void*)&slots, (void*)&ps.tws, (void*)&ps.twsB, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                      (void*)&ps.otw_lo, (void*)&ps.otw_hi, p->is_double ? (void*)&scd : (void*)&scf, (void*)&counters};
+      if (ce == cudaSuccess)
+        ce = cudaLaunchCooperativeKernel(ps.bz->func, dim3((unsigned)ps.band_grid), dim3(ps.bz->threads), args, ps.bz->smem, stream);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (ps.kind == PK_COPY) {
       long long nl = 0;
       ce = launch_copy_scale(p->is_double, src, dst, p->total, sc, stream, &nl);
@@ -1301,6 +1461,7 @@ int b200fftPeerClose(void* ptr) {
 int b200fftDestroy(b200fftHandle p) {
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
   p->magic = 0;
+  if (p->fallback) b200fftDestroy(p->fallback);
   for (auto& ps : p->passes) destroy_generic(&ps.gp);
   // cudaFree is legal from any thread; if the owning context is already gone the error is benign
   for (void* d : p->dev_allocs) cudaFree(d);

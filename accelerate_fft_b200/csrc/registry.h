@@ -33,6 +33,20 @@ struct FusedEntry {
   int threads;
   size_t smem;
 };
+// two phases fused through L2, persistent + TMA-fed (band_kernel.cuh)
+struct BandEntry {
+  int is_double;
+  int mode;           // BandMode: 0 strided axis, 1 contiguous rows (transposing second phase)
+  int outer;          // phase B multiplies by the outer four-step twiddle
+  int N1, N2, TLA, TLB;
+  KernelEntry a, b;   // stage-twiddle description of the two phases (func unused)
+  int threads;
+  size_t smem;
+  const void* func;
+};
+const BandEntry* find_band(int is_double, int mode, int outer, int N1, int N2);
+void register_band(void (*add)(const BandEntry&));
+
 const FusedEntry* find_fused(int is_double, int NA, int flavA, int twA, int NB, int flavB);
 void register_fused(void (*add)(const FusedEntry&));
 

@@ -489,6 +489,14 @@ def test_edge_cases(af):
     t = torch.randn(32, 48, dtype=torch.complex64, device="cuda").t()
     y = af.fft("Forward", t)
     assert rel_l2(y.cpu().numpy(), np.fft.fft(t.cpu().numpy().astype(np.complex128), axis=-1)) < 1e-5
+    # lazy conj / neg views (x.conj(), x.mH) share storage with the plain tensor: they must be materialised, not ignored
+    c = torch.randn(8, 64, dtype=torch.complex64, device="cuda")
+    ref = np.fft.fft(np.conj(c.cpu().numpy()).astype(np.complex128), axis=-1)
+    assert c.conj().is_conj()
+    assert rel_l2(af.fft("Forward", c.conj()).cpu().numpy(), ref) < 1e-5
+    assert rel_l2(af.fft2D("Forward", c.conj()).cpu().numpy(), np.fft.fft2(np.conj(c.cpu().numpy()).astype(np.complex128))) < 1e-5
+    hc = torch.randn(4, 32, dtype=torch.complex128).conj()
+    assert rel_l2(af.run_host_seq("fft", ["Forward"], hc).numpy(), np.fft.fft(hc.resolve_conj().numpy(), axis=-1)) < 1e-12
 
 
 def test_host_buffer_entry_and_fused_inverse(af, oracle):
