@@ -18,18 +18,11 @@ static BandEntry make_band() {
   return e;
 }
 
-#ifndef B200FFT_BAND_G
-#define B200FFT_BAND_G 6
-#endif
-#ifndef B200FFT_BAND_NSTG
-#define B200FFT_BAND_NSTG 2
-#endif
-
 void register_band(void (*add)(const BandEntry&)) {
-  constexpr int G = B200FFT_BAND_G, NS = B200FFT_BAND_NSTG;
   using F64 = Cfg<float, 64, 16, 32, 1, 16, 4>;      // 128 threads, 32 lines (256 B runs), 16 KB tiles
   using F128 = Cfg<float, 128, 16, 16, 1, 16, 8>;    // 128 threads, 16 lines (128 B runs), 16 KB tiles
-  // strided axis of N1*N2 points: cfg3's column axis 8192 = 64 x 128; 4096 and 16384 for the neighbouring sizes
-  add(make_band<BandCfg<F64, F128, MODE_STRIDED, false, G, NS>>());
+  // strided axis of N1*N2 points (6 groups, 7 landing stages; 4 groups / 9 stages measured equal within 3 %):
+  add(make_band<BandCfg<F64, F128, MODE_STRIDED, false, 6, 7>>());     // 8192 = 64 x 128: cfg3's column axis
+  // (4096 = 64 x 64 measured equal to the two unfused passes -- 141 vs 138 us on 4096^2 -- and is left to them)
 }
 }  // namespace b200fft

@@ -206,6 +206,39 @@ def _np_fft2(mode, x):
     return np.fft.fft2(x128) if mode == "Forward" else np.fft.ifft2(x128) * (1 if mode == "Inverse" else x.size)
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape", [(8192, 128), (8192, 512), (8192, 96)])
+def test_band_kernel_l2_fused_column_axis(af, oracle, mode, shape):
+    """Strided axes of 8192 points (c64): both four-step phases in ONE persistent TMA-fed launch with the
+    intermediate in L2 scratch slots (band_kernel.cuh) -- the default plan for cfg3's column axis.  Against the oracle's
+    fft2D; the same transform planned without the band pass (B200FFT_BAND=0) must agree to rounding; a width that is not
+    a multiple of the band (96 columns) and a buffer that is only 8-byte aligned take the fallback plan."""
+    import torch
+    h, w = shape
+    rng = np.random.default_rng(h + w)
+    x = rand_complex(rng, (h, w), np.complex64)
+    p = af.Plan("2d", [h, w], af.C2C, 1)
+    desc = p.describe()
+    p.destroy()
+    assert ("band A[" in desc) == (w % 32 == 0), desc
+    y = gpu(af, "fft2D", mode, x)
+    assert rel_l2(y, oracle.fft2D(mode, x, threads=8)) <= bar(np.complex64, x.size)
+    with _env(af, B200FFT_BAND="0"):
+        y0 = gpu(af, "fft2D", mode, x)
+    assert rel_l2(y, y0) <= 4e-7
+    if w % 32 == 0:
+        # 8-byte aligned (not 16) input and output: TMA cannot serve them, the band-free fallback plan does
+        buf = torch.empty(h * w + 1, dtype=torch.complex64, device="cuda")
+        xin = buf[1:].view(h, w)
+        xin.copy_(torch.from_numpy(x))
+        obuf = torch.empty(h * w + 1, dtype=torch.complex64, device="cuda")
+        out = obuf[1:].view(h, w)
+        pl = af.Plan("2d", [h, w], af.C2C, 1)
+        pl.exec(xin, out, af.FORWARD)
+        pl.destroy()
+        assert rel_l2(out.cpu().numpy(), oracle.fft2D("Forward", x, threads=8)) <= bar(np.complex64, x.size)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode", MODES)
 def test_cluster_column_kernel(af, oracle, dtype, mode):
