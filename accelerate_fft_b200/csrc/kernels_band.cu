@@ -24,5 +24,11 @@ void register_band(void (*add)(const BandEntry&)) {
   // strided axis of N1*N2 points (6 groups, 7 landing stages; 4 groups / 9 stages measured equal within 3 %):
   add(make_band<BandCfg<F64, F128, MODE_STRIDED, false, 6, 7>>());     // 8192 = 64 x 128: cfg3's column axis
   // (4096 = 64 x 64 measured equal to the two unfused passes -- 141 vs 138 us on 4096^2 -- and is left to them)
+  add(make_band<BandCfg<F128, F128, MODE_STRIDED, false, 6, 7>>());    // 16384 = 128 x 128 columns
+  // large contiguous 1D transforms, N = Nout x 16384 in TWO HBM round trips (cfg4: 2^28 = 2^14 x 2^14):
+  //   pass 1 = the Nout-point strided axis + the outer four-step twiddle, pass 2 = 16384-point rows, transposed store
+  add(make_band<BandCfg<F64, F128, MODE_STRIDED, true, 6, 7>>());
+  add(make_band<BandCfg<F128, F128, MODE_STRIDED, true, 6, 7>>());
+  add(make_band<BandCfg<F128, F128, MODE_ROWS, false, 6, 6>>());   // (row-layout exchange buffers: 6 landing stages fit)
 }
 }  // namespace b200fft

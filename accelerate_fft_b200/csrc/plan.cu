@@ -713,6 +713,90 @@ struct Builder {
     return true;
   }
 
+  // contiguous rows [O][R][M], M = N1*N2 (band_kernel.cuh, MODE_ROWS): a band is TLB adjacent rows (one contiguous piece of the
+  // array); phase A = N1-point columns inside each row (+ twiddle w_M^(k1 n2)), phase B = N2-point rows of the intermediate with
+  // the transposed store X[o*R*M + r + R*(k1 + N1*k2)] -- the LAST pass of a big four-step whose first pass left row r = the
+  // outer output index.  Not in place.
+  bool try_band_rows(long long O, long long R, long long M) {
+    if (no_band || (getenv("B200FFT_BAND") && atoi(getenv("B200FFT_BAND")) == 0)) return false;
+    const BandEntry* bz = nullptr;
+    long long N1 = 0, N2 = 0;
+    for (long long n1 : {128LL, 64LL, 256LL}) {
+      if (M % n1) continue;
+      bz = find_band(p->is_double, MODE_ROWS, 0, (int)n1, (int)(M / n1));
+      if (bz) { N1 = n1; N2 = M / n1; break; }
+    }
+    if (!bz) return false;
+    const long long esz = (long long)esize(p);
+    const long long TLB = bz->TLB, TLA = bz->TLA;
+    if (R % TLB || N2 % TLA) return false;
+    const long long rows = O * R;
+    if (2 * N2 >= (1LL << 32) || rows >= (1LL << 31) || rows * M * esz >= (1LL << 40)) return false;
+    const long long nbi = R / TLB, nbands = O * nbi;
+    const long long a_ncg = N2 / TLA, nA = TLB * a_ncg, nB = N1;
+    if (nbands >= (1LL << 24) || nbands * (nA + nB) >= (1LL << 31)) return false;
+    if (nbands * (nA + nB) < 4 * 148) return false;
+    if ((N1 * bz->b.N / bz->b.E) * R * esz >= (1LL << 32)) return false;   // 32-bit byte step between a thread's stores
+    Pass ps;
+    ps.kind = PK_BAND;
+    ps.bz = bz;
+    BandParams bp{};
+    bp.nbands = (int)nbands; bp.nA = (int)nA; bp.nB = (int)nB;
+    bp.la = 0;
+    bp.nslots = env_int("B200FFT_BAND_SLOTS", 24);
+    if (bp.nslots < 2) bp.nslots = 2;
+    if (bp.nslots > bp.nbands) bp.nslots = bp.nbands;
+    bp.nbi = (int)nbi;
+    bp.a_ncg = (int)a_ncg;
+    bp.slot_elems = TLB * M;
+    bp.out_bo = R * M; bp.out_bi = TLB; bp.out_ks = R;
+    bp.wb = 0;
+    bp.debug = env_int("B200FFT_BAND_DEBUG", 0);
+    ps.tws = make_stage_twiddles(p, &bz->a);
+    ps.twsB = make_stage_twiddles(p, &bz->b);
+    make_fourstep_tables(p, M, &bp.tw_lo_bits, &ps.tw_lo, &ps.tw_hi);
+    bp.tw_lo_n = 1 << bp.tw_lo_bits;
+    bp.tw_hi_n = (int)((M + bp.tw_lo_n - 1) / bp.tw_lo_n);
+    if (bp.tw_lo_n + bp.tw_hi_n > 512) return false;
+    ps.bp = bp;
+    // the rows as a tensor {2 N2, N1, rows, 1}; a phase-A tile is the box {2 TLA, N1, 1, 1}
+    ps.tm_dims[0] = 2ull * (unsigned long long)N2; ps.tm_dims[1] = (unsigned long long)N1; ps.tm_dims[2] = (unsigned long long)rows; ps.tm_dims[3] = 1;
+    ps.tm_strides[0] = (unsigned long long)(N2 * esz); ps.tm_strides[1] = (unsigned long long)(M * esz); ps.tm_strides[2] = (unsigned long long)(rows * M * esz);
+    ps.tm_box[0] = 2u * (unsigned)TLA; ps.tm_box[1] = (unsigned)N1; ps.tm_box[2] = 1; ps.tm_box[3] = 1;
+    ps.inplace_ok = false;
+    ps.ntiles = nbands * (nA + nB);
+    const size_t need = counters_bytes(bp.nbands) + (size_t)bp.nslots * (size_t)bp.slot_elems * esize(p);
+    if (need > p->band_bytes) p->band_bytes = need;
+    char buf[384];
+    snprintf(buf, sizeof buf,
+             "4step-rows: band A[N=%d col+tw TL=%d] -> L2 slots -> B[N=%d trans TL=%d] | persistent TMA-fed, threads=%d smem=%zu bands=%lld x %lld rows "
+             "tiles/band=%lld+%lld slot=%.1f MiB x%d",
+             bz->N1, bz->TLA, bz->N2, bz->TLB, bz->threads, bz->smem, nbands, TLB, nA, nB, (double)bp.slot_elems * esize(p) / 1048576.0, bp.nslots);
+    ps.desc = buf;
+    push(ps);
+    return true;
+  }
+
+  // contiguous lines [O][N], N = Nout * M: TWO HBM round trips, each a band pass with its intermediate in L2 --
+  //   pass 1: the Nout-point strided axis of [O][Nout][M] + the outer twiddle w_N^(kout * m)  (MODE_STRIDED, OUTER)
+  //   pass 2: the M-point rows with the transposed store X[kout + Nout * km]                  (MODE_ROWS)
+  // cfg4 (2^28 = 2^14 x 2^14): replaces the three lines passes (3 HBM round trips, strict fraction capped at 0.67).
+  bool try_band_contig2(long long O, long long N) {
+    if (no_band || (getenv("B200FFT_BAND") && atoi(getenv("B200FFT_BAND")) == 0)) return false;
+    if (getenv("B200FFT_BAND_1D") && atoi(getenv("B200FFT_BAND_1D")) == 0) return false;
+    for (long long M : {16384LL}) {
+      if (N % M) continue;
+      const long long Nout = N / M;
+      if (Nout < 4096 || Nout > 16384) continue;
+      const size_t n0 = p->passes.size();
+      const size_t bb0 = p->band_bytes;
+      if (try_band_strided(O, Nout, M, true, N, 0) && try_band_rows(O, Nout, M)) return true;
+      p->passes.resize(n0);
+      p->band_bytes = bb0;
+    }
+    return false;
+  }
+
   // longest strided axis done in one pass (>= 64 B runs)
   int max_col_n() const { return env_int("B200FFT_MAX_COL_N", 2048); }
   int max_row_n() const { return p->is_double ? 8192 : 16384; }  // largest N with a row kernel
@@ -818,6 +902,7 @@ struct Builder {
       return;
     }
     if (N > lim * lim * lim) { err = B200FFT_NOT_SUPPORTED; return; }
+    if (try_band_contig2(O, N)) return;
     // three factors: n = n1*M + n2*N3 + n3 (M = N2*N3), k = k1 + N1*k2 + N1*N2*k3
     int a = lg / 3, b = (lg - a) / 2, c = lg - a - b;
     long long N1 = 1LL << c, N2 = 1LL << b, N3 = 1LL << a;  // largest first: column tiles are cheapest to keep big
