@@ -675,8 +675,9 @@ struct Builder {
     BandParams bp{};
     bp.nbands = (int)nbands; bp.nA = (int)nA; bp.nB = (int)nB;
     bp.la = 0;   // (unused by the two-list loader: phase A runs ahead as far as the slots allow)
-    bp.nslots = env_int("B200FFT_BAND_SLOTS", 24);   // 24 x 2 MiB: measured optimum on cfg3 (12: 541 us, 16: 504, 24: 472, 32: 486, 48: 554)
-    if (bp.nslots < 2) bp.nslots = 2;
+    // 48 MiB of slots: measured optimum on cfg3 with 2 MiB slots (12: 541 us, 16: 504, 24: 472, 32: 486, 48: 554)
+    bp.nslots = env_int("B200FFT_BAND_SLOTS", (int)((48LL << 20) / (N * Wb * esz)));
+    if (bp.nslots < 4) bp.nslots = 4;
     if (bp.nslots > bp.nbands) bp.nslots = bp.nbands;
     bp.nbi = (int)nbi;
     bp.a_ncg = (int)(Wb / bz->TLA);
@@ -743,8 +744,8 @@ struct Builder {
     BandParams bp{};
     bp.nbands = (int)nbands; bp.nA = (int)nA; bp.nB = (int)nB;
     bp.la = 0;
-    bp.nslots = env_int("B200FFT_BAND_SLOTS", 24);
-    if (bp.nslots < 2) bp.nslots = 2;
+    bp.nslots = env_int("B200FFT_BAND_SLOTS", (int)((48LL << 20) / (TLB * M * esz)));
+    if (bp.nslots < 4) bp.nslots = 4;
     if (bp.nslots > bp.nbands) bp.nslots = bp.nbands;
     bp.nbi = (int)nbi;
     bp.a_ncg = (int)a_ncg;
@@ -783,7 +784,10 @@ struct Builder {
   // cfg4 (2^28 = 2^14 x 2^14): replaces the three lines passes (3 HBM round trips, strict fraction capped at 0.67).
   bool try_band_contig2(long long O, long long N) {
     if (no_band || (getenv("B200FFT_BAND") && atoi(getenv("B200FFT_BAND")) == 0)) return false;
-    if (getenv("B200FFT_BAND_1D") && atoi(getenv("B200FFT_BAND_1D")) == 0) return false;
+    // Opt-in (B200FFT_BAND_1D=1).  Measured on B200 (profiles/r02_band_experiments.txt): correct and two HBM round trips
+    // (each band pass moves its 2 GiB in ~1.2 ms), but 2.39-2.42 ms against 2.35 ms for the three lines passes below: a band
+    // pass costs four SM<->L2 transfers per element, and that, not HBM, is what bounds it.
+    if (!(getenv("B200FFT_BAND_1D") && atoi(getenv("B200FFT_BAND_1D")))) return false;
     for (long long M : {16384LL}) {
       if (N % M) continue;
       const long long Nout = N / M;

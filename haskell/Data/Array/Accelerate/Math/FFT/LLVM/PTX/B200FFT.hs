@@ -24,6 +24,7 @@ module Data.Array.Accelerate.Math.FFT.LLVM.PTX.B200FFT (
 
 import Control.Exception
 import Control.Monad                                                ( when )
+import Data.Hashable
 import Data.Int
 import Foreign.C.String
 import Foreign.C.Types
@@ -49,6 +50,10 @@ instance Enum Type where
   toEnum 0x69  = Z2Z
   toEnum x     = error ("B200FFT.Type.toEnum: " ++ show x)
 
+-- | The plan caches key on the full (context, shape, type) tuple (haskell/patch/0001, PTX/Plans.hs:41,72).
+instance Hashable Type where
+  hashWithSalt s = hashWithSalt s . fromEnum
+
 -- | Direction; un-normalised both ways (FFT.hs applies the 'Inverse' scale afterwards).
 data Mode = Forward | Inverse
   deriving (Eq, Show)
@@ -69,10 +74,12 @@ foreign import ccall safe   "b200fftPlan1d"     c_plan1d     :: Ptr (Ptr ()) -> 
 foreign import ccall safe   "b200fftPlan2d"     c_plan2d     :: Ptr (Ptr ()) -> Int64 -> Int64 -> CInt -> IO CInt
 foreign import ccall safe   "b200fftPlan3d"     c_plan3d     :: Ptr (Ptr ()) -> Int64 -> Int64 -> Int64 -> CInt -> IO CInt
 foreign import ccall safe   "b200fftPlanMany1d" c_planMany1d :: Ptr (Ptr ()) -> Int64 -> Int64 -> CInt -> IO CInt
--- exec only enqueues kernels on the stream and never blocks: unsafe call is appropriate
-foreign import ccall unsafe "b200fftExec"       c_exec       :: Ptr () -> Ptr () -> Ptr () -> CInt -> Ptr () -> IO CInt
-foreign import ccall unsafe "b200fftExecScaled" c_execScaled :: Ptr () -> Ptr () -> Ptr () -> CInt -> CDouble -> Ptr () -> IO CInt
-foreign import ccall unsafe "b200fftExecShifted" c_execShifted :: Ptr () -> Ptr () -> Ptr () -> CInt -> CDouble -> Ptr () -> IO CInt
+-- exec only enqueues kernels, but it takes the scratch-pool mutex, may create the pool on first use and its first launch
+-- loads the CUDA module lazily: a `safe` call keeps the GHC capability and the stop-the-world GC free meanwhile, at a cost
+-- that is negligible next to a kernel launch
+foreign import ccall safe   "b200fftExec"       c_exec       :: Ptr () -> Ptr () -> Ptr () -> CInt -> Ptr () -> IO CInt
+foreign import ccall safe   "b200fftExecScaled" c_execScaled :: Ptr () -> Ptr () -> Ptr () -> CInt -> CDouble -> Ptr () -> IO CInt
+foreign import ccall safe   "b200fftExecShifted" c_execShifted :: Ptr () -> Ptr () -> Ptr () -> CInt -> CDouble -> Ptr () -> IO CInt
 foreign import ccall safe   "b200fftDestroy"    c_destroy    :: Ptr () -> IO CInt
 foreign import ccall unsafe "b200fftErrorString" c_errorString :: CInt -> IO CString
 

@@ -9,6 +9,8 @@ restatement of the reference's pure-Accelerate path:
   * adhoc_fft / adhoc_fft2d / adhoc_fft3d  <- Adhoc.hs:37-48 (+ FFT.hs:136-138,166-187)
   * fft / fft1D / fft2D / fft3D wrappers that add the `Inverse` scaling of FFT.hs:83,110,141,172
   * exact_dft / exact_bin: the long-double definition of the transform (Mode.hs:21-26).
+  * dft / idft (dft_definition.c): the reference's own definition module, DFT.hs:42-59 + DFT/Roots.hs:26-51, in the
+    working precision -- a second oracle that shares no algorithm with the first.
 PARITY STATUS: unpinned by reference-held vectors (the reference has none); see adhoc_oracle.c.
 """
 import ctypes
@@ -30,7 +32,7 @@ def sign_of_mode(mode):
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("adhoc_oracle.c", "adhoc_impl.inc")]
+    srcs = [os.path.join(_HERE, f) for f in ("adhoc_oracle.c", "adhoc_impl.inc", "dft_definition.c")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
     return so
@@ -47,6 +49,9 @@ def _lib():
             getattr(lib, "adhoc_fft3d_" + suf).argtypes = [i, sz, sz, sz, vp, vp, i]
             for n in ("adhoc_fft_", "adhoc_fft2d_", "adhoc_fft3d_"):
                 getattr(lib, n + suf).restype = None
+        for suf in ("f32", "f64"):
+            getattr(lib, "dft_definition_" + suf).argtypes = [i, sz, sz, vp, vp]
+            getattr(lib, "dft_definition_" + suf).restype = None
         lib.exact_dft.argtypes = [i, sz, sz, vp, vp]
         lib.exact_dft.restype = None
         lib.exact_bin.argtypes = [i, sz, sz, sz, vp, vp]
@@ -123,6 +128,25 @@ def fft2D(mode, a, threads=1):
 def fft3D(mode, a, threads=1):
     """FFT.hs:150-173: scale = size arr."""
     return _scaled(mode, adhoc_fft3d(sign_of_mode(mode), a, threads), a.size)
+
+
+def _dft_definition(inverse, a):
+    a = np.ascontiguousarray(a)
+    out = np.empty_like(a)
+    n = a.shape[-1]
+    if a.size:
+        getattr(_lib(), "dft_definition_" + _suf(a))(inverse, a.size // n, n, _ptr(a), _ptr(out))
+    return out
+
+
+def dft(a):
+    """DFT.hs:42-45 `dft` (roots: DFT/Roots.hs:26-36) along the innermost axis, in the precision of `a`.  O(n^2)."""
+    return _dft_definition(0, a)
+
+
+def idft(a):
+    """DFT.hs:50-59 `idft` (roots: DFT/Roots.hs:41-51; divides by n), in the precision of `a`.  O(n^2)."""
+    return _dft_definition(1, a)
 
 
 def exact_dft(sign, a):
