@@ -13,6 +13,8 @@ FORWARD = -1
 INVERSE = 1
 
 _lib = None
+# b200fftAllgatherFn: int (*)(void* ctx, const void* send, void* recv, size_t bytes)
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
 EXPORTS = [
     "b200fftPlan1d", "b200fftPlan2d", "b200fftPlan3d", "b200fftPlanMany1d", "b200fftExec",
@@ -22,6 +24,8 @@ EXPORTS = [
     "accfft_set_fused_inverse", "accfft_plan_cache_size", "accfft_plan_cache_clear",
     "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack", "b200fftTrimScratch",
     "b200fftExecShifted", "accfft_centre", "accfft_shift", "accfft_fft_centred",
+    "b200fftExecScatterOn", "b200fftPlanAxisView",
+    "b200fftPlanSlab3d", "b200fftExecSlab", "b200fftSlabNaturalBuffer", "b200fftSlabTune", "b200fftDestroySlab",
     "b200fftExecScatter", "b200fftPeerAlloc", "b200fftPeerFree", "b200fftPeerExport", "b200fftPeerOpen", "b200fftPeerClose",
 ]
 
@@ -91,6 +95,13 @@ def lib():
     L.accfft_shift.argtypes = [i, pi64, i, i, vp, vp, vp]
     L.accfft_fft_centred.argtypes = [i, i, pi64, i, vp, vp, vp]
     L.b200fftExecScatter.argtypes = [vp, vp, pvp, i, i64, i64, i, d, vp]
+    L.b200fftExecScatterOn.argtypes = [vp, vp, pvp, i, i64, i64, i, d, i, vp]
+    L.b200fftPlanAxisView.argtypes = [pvp, i64, i64, i64, i64, i64, i]
+    L.b200fftPlanSlab3d.argtypes = [pvp, i64, i64, i64, i, i, i, i, ALLGATHER_FN, vp]
+    L.b200fftExecSlab.argtypes = [vp, vp, vp, i, d, i, vp]
+    L.b200fftSlabNaturalBuffer.argtypes = [vp, pvp]
+    L.b200fftSlabTune.argtypes = [vp, i, i, i]
+    L.b200fftDestroySlab.argtypes = [vp]
     L.b200fftPeerAlloc.argtypes = [pvp, ctypes.c_size_t]
     L.b200fftPeerFree.argtypes = [vp]
     L.b200fftPeerExport.argtypes = [vp, ctypes.c_char_p]

@@ -372,4 +372,20 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
   fft_lines_tile<K, LLF, SLF, TW4, false, 0, PRE2>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
 }
 
+// The same tile function under a grid-stride loop: the launch decides how many CTAs (hence SMs) the pass occupies.  Used by
+// the slab-decomposed 3D transform, whose NVLink-bound scatter pass needs only a fraction of the SMs and leaves the rest to
+// the HBM-bound passes running beside it on other streams (slab.cu).
+template <class K, bool LLF, bool SLF, bool TW4>
+__global__ void __launch_bounds__(K::THREADS, K::MINB)
+fft_lines_loop_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
+                      const cpx_t<typename K::real>* __restrict__ tws, const cpx_t<typename K::real>* __restrict__ tw_lo,
+                      const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale, unsigned ntiles) {
+  using C = cpx_t<typename K::real>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    fft_lines_tile<K, LLF, SLF, TW4, false, 0, false>(g, tile, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
+    __syncthreads();   // the exchange space is re-used by the next tile
+  }
+}
+
 }  // namespace b200fft

@@ -25,6 +25,9 @@ template <class K, bool LLF, bool SLF, bool TW4, bool PRE2 = false>
 KernelEntry make_entry() {
   KernelEntry e = describe_cfg<K, LLF, SLF, TW4, PRE2>();
   e.func = reinterpret_cast<const void*>(&fft_lines_kernel<K, LLF, SLF, TW4, PRE2>);
+  // strided-axis kernels of 128+ points (the ones a scatter pass can use) also come as a grid-stride loop
+  if constexpr (LLF && SLF && !TW4 && !PRE2 && K::N >= 128 && K::S >= 2)
+    e.loop_func = reinterpret_cast<const void*>(&fft_lines_loop_kernel<K, LLF, SLF, TW4>);
   return e;
 }
 

@@ -811,6 +811,19 @@ struct Builder {
     axis_impl(O, N, I);
     if (!err && p->passes.size() > before) p->passes.back().axis_last = true;
   }
+  // A strided axis seen through a window: element (o, n, i) at o*os + n*ns + i, i < I (I may be a sub-range of the real row).
+  // One in-place column pass only (power-of-two N <= max_col_n): the building block of the chunked slab transform.
+  void axis_view(long long O, long long N, long long I, long long os, long long ns) {
+    if (err) return;
+    if (O >= (1LL << 31) || I >= (1LL << 31) || !is_pow2(N) || N < 2 || N > max_col_n()) { err = B200FFT_NOT_SUPPORTED; return; }
+    Geom g{};
+    g.nb = 1; g.no = (int)O; g.nl = (int)I;
+    g.ios = os; g.ils = 1; g.ins = ns;
+    g.oos = os; g.ols = 1; g.ons = ns;
+    g.tw_div = 1;
+    if (!lines_pass((int)N, FL_COL, false, g, 0, true, 0, "cols-view")) { if (!err) err = B200FFT_NOT_SUPPORTED; return; }
+    p->passes.back().axis_last = true;
+  }
   void axis_impl(long long O, long long N, long long I) {
     if (err || N == 1) return;
     if (O >= (1LL << 31) || I >= (1LL << 31) || N >= (1LL << 31)) { err = B200FFT_INVALID_SIZE; return; }
@@ -1250,6 +1263,16 @@ int b200fftPlanAxis(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner
                      [&](Builder& b) { b.axis(outer, n, inner); });
 }
 
+int b200fftPlanAxisView(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner, int64_t outer_stride, int64_t n_stride, int type) {
+  if (!plan) return B200FFT_INVALID_VALUE;
+  int dbl;
+  if (check_type(type, &dbl)) return B200FFT_INVALID_TYPE;
+  if (n < 1 || outer < 1 || inner < 1 || n_stride < inner || outer_stride < 0) return B200FFT_INVALID_SIZE;
+  if (int e = have_device()) return e;
+  return create_plan(plan, [&](b200fft_plan_s* p) { p->is_double = dbl; p->rank = 1; p->dims[0] = n; p->batch = outer * inner; p->total = n * outer * inner; },
+                     [&](Builder& b) { b.axis_view(outer, n, inner, outer_stride, n_stride); });
+}
+
 int b200fftPlan1d(b200fftHandle* plan, int64_t n, int type, int64_t batch) { return b200fftPlanMany1d(plan, n, batch, type); }
 
 int b200fftPlan2d(b200fftHandle* plan, int64_t h, int64_t w, int type) {
@@ -1487,6 +1510,12 @@ int b200fftExec(b200fftHandle plan, const void* in, void* out, int direction, b2
 // sits at o*out_outer_stride + nl*out_n_stride + i.  See include/b200fft.h.
 int b200fftExecScatter(b200fftHandle p, const void* in, void* const* outs, int npeers, int64_t out_outer_stride,
                        int64_t out_n_stride, int direction, double scale, b200fftStream stream_) {
+  return b200fftExecScatterOn(p, in, outs, npeers, out_outer_stride, out_n_stride, direction, scale, 0, stream_);
+}
+// max_ctas > 0: the pass runs as a grid-stride loop of at most that many CTAs (it then occupies that many SMs and leaves the
+// others to kernels running beside it on other streams); 0 = one CTA per tile.
+int b200fftExecScatterOn(b200fftHandle p, const void* in, void* const* outs, int npeers, int64_t out_outer_stride,
+                         int64_t out_n_stride, int direction, double scale, int max_ctas, b200fftStream stream_) {
   if (!p || p->magic != 0xB200FF7u) return B200FFT_INVALID_PLAN;
   if (!in || !outs || npeers < 1 || npeers > 16) return B200FFT_INVALID_VALUE;
   if (direction != B200FFT_FORWARD && direction != B200FFT_INVERSE) return B200FFT_INVALID_VALUE;
@@ -1512,7 +1541,14 @@ int b200fftExecScatter(b200fftHandle p, const void* in, void* const* outs, int n
   cudaError_t ce;
   // NVLink wants long runs: the lock-step kernel stores 128 B per row (TL = 16), the pipelined one 64 B -- measured on
   // 2 x B200, 1024^3: 6.24 ms against 8.30 ms per transform -- so the pipelined kernel only serves a single target
-  if (npeers == 1 && ps.pipe && ps.pipe->CS == 1 && ((uintptr_t)in & 15) == 0) {
+  if (max_ctas > 0 && ps.k->loop_func) {
+    if (ps.k->smem > 48 * 1024) cudaFuncSetAttribute(ps.k->loop_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem);
+    unsigned nt = (unsigned)ps.ntiles;
+    void* args[] = {&g, (void*)&in, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
+                    p->is_double ? (void*)&scd : (void*)&scf, (void*)&nt};
+    const long long grid = ps.ntiles < max_ctas ? ps.ntiles : max_ctas;
+    ce = cudaLaunchKernel(ps.k->loop_func, dim3((unsigned)grid), dim3(ps.k->threads), args, ps.k->smem, stream);
+  } else if (npeers == 1 && ps.pipe && ps.pipe->CS == 1 && ((uintptr_t)in & 15) == 0) {
     g.ntl = ps.pipe_ntl;
     void* args[] = {&g, (void*)&in, (void*)&dst, (void*)&ps.ptws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
                     p->is_double ? (void*)&scd : (void*)&scf, (void*)&ps.pctw};

@@ -23,6 +23,7 @@ struct KernelEntry {
   int G, NS;       // FL_RING: thread groups per CTA, stage buffers
   int CS, N1;      // FL_CLUSTER: cluster size and per-CTA sub-length (N = N1*CS; S, rad, tw_len describe N1)
   const void* func;
+  const void* loop_func;   // same kernel as a grid-stride loop over the tiles (last argument: tile count); null if not instantiated
 };
 
 

@@ -273,6 +273,70 @@ class PeerSlabFFT3D:
             p.destroy()
 
 
+class SlabPlan:
+    """ctypes face of the C-ABI slab transform (include/b200fft.h: b200fftPlanSlab3d / b200fftExecSlab, csrc/slab.cu): the
+    x / y-scatter / z pipeline, the peer mappings and the flag barriers all live in the library; this class only supplies
+    the bootstrap all-gather (torch.distributed) and hands device pointers over.  Collective: every rank of `group`
+    constructs it and calls it with the same arguments in the same order."""
+
+    NATURAL_OUT, TRANSPOSED_OUT = 0, 1
+
+    def __init__(self, d, h, w, dtype, group=None, natural=True):
+        import torch
+        import torch.distributed as dist
+        from ._lib import ALLGATHER_FN, C2C, Z2Z, check, lib
+        self.torch, self.lib, self.check = torch, lib(), check
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.geom = SlabGeometry(d, h, w, self.world)
+        self.dtype = dtype
+        self.natural = natural
+        on_gpu = dist.get_backend(group) == "nccl"
+
+        def allgather(_ctx, send, recv, nbytes):
+            try:
+                mine = torch.frombuffer(bytearray(ctypes.string_at(send, nbytes)), dtype=torch.uint8)
+                if on_gpu:
+                    mine = mine.cuda()
+                parts = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(parts, mine, group=group)
+                blob = b"".join(bytes(q.cpu().numpy().tobytes()) for q in parts)
+                ctypes.memmove(recv, blob, len(blob))
+                return 0
+            except Exception:      # the C side turns this into B200FFT_EXEC_FAILED
+                return 1
+
+        self._cb = ALLGATHER_FN(allgather)     # keep the trampoline alive for the duration of the call
+        hnd = ctypes.c_void_p()
+        check(self.lib.b200fftPlanSlab3d(ctypes.byref(hnd), d, h, w, C2C if dtype == torch.complex64 else Z2Z, self.rank, self.world,
+                                         1 if natural else 0, self._cb, None), "b200fftPlanSlab3d")
+        self.h = hnd
+
+    def tune(self, plane_chunks=1, col_chunks=1, y_ctas=0):
+        self.check(self.lib.b200fftSlabTune(self.h, plane_chunks, col_chunks, y_ctas), "b200fftSlabTune")
+        return self
+
+    def __call__(self, mode, x_local, transposed_out=False, out=None):
+        from . import FORWARD, INVERSE, Inverse, Forward
+        g, torch = self.geom, self.torch
+        if tuple(x_local.shape) != (g.dl, g.h, g.w) or x_local.dtype != self.dtype or not x_local.is_cuda:
+            raise ValueError("SlabPlan: expected this rank's (%d, %d, %d) %s z-slab on the device" % (g.dl, g.h, g.w, self.dtype))
+        x_local = x_local.resolve_conj().resolve_neg().contiguous()
+        shape = (g.d, g.hl, g.w) if transposed_out else (g.dl, g.h, g.w)
+        if out is None:
+            out = torch.empty(shape, dtype=self.dtype, device="cuda")
+        sign = FORWARD if mode == Forward else INVERSE
+        scale = 1.0 / float(g.d * g.h * g.w) if mode == Inverse else 1.0      # FFT.hs:155,172
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.check(self.lib.b200fftExecSlab(self.h, x_local.data_ptr(), out.data_ptr(), sign, scale,
+                                            self.TRANSPOSED_OUT if transposed_out else self.NATURAL_OUT, st), "b200fftExecSlab")
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.b200fftDestroySlab(self.h)
+            self.h = None
+
+
 def bench_slab(args, af, dist, rank, local, world, desc, measured_peak, ClockSampler):
     """bench.py --config cfg5 at N>1 GPUs: 1024^3 c64, z-slabs, strong scaling."""
     import json

@@ -107,12 +107,52 @@ int b200fftSlabUnpack(int type, const void* src, void* dst, int64_t dl, int64_t 
  * (a barrier on all ranks before the buffers are overwritten and after the kernel has finished). */
 int b200fftExecScatter(b200fftHandle plan, const void* in, void* const* outs, int npeers, int64_t out_outer_stride,
                        int64_t out_n_stride, int direction, double scale, b200fftStream stream);
+/* Same; max_ctas > 0 runs the pass as a grid-stride loop of at most that many CTAs, so that an NVLink-bound scatter pass
+ * occupies only that many SMs and HBM-bound passes on other streams run beside it (0 = one CTA per tile). */
+int b200fftExecScatterOn(b200fftHandle plan, const void* in, void* const* outs, int npeers, int64_t out_outer_stride,
+                         int64_t out_n_stride, int direction, double scale, int max_ctas, b200fftStream stream);
+/* b200fftPlanAxis through a window: element (o, k, i) of the axis sits at o*outer_stride + k*n_stride + i with i < inner,
+ * i.e. `inner` may be a sub-range of the real rows (a chunk of columns).  Power-of-two n <= 2048 (one in-place pass). */
+int b200fftPlanAxisView(b200fftHandle* plan, int64_t outer, int64_t n, int64_t inner, int64_t outer_stride, int64_t n_stride,
+                        int type);
 /* Device buffers another process of the same box can map (CUDA IPC, 64-byte handles exchanged by the caller). */
 int b200fftPeerAlloc(void** ptr, size_t bytes);
 int b200fftPeerFree(void* ptr);
 int b200fftPeerExport(void* ptr, unsigned char handle[64]);
 int b200fftPeerOpen(const unsigned char handle[64], void** ptr);
 int b200fftPeerClose(void* ptr);
+
+/*
+ * Multi-GPU entry point: the slab-decomposed 3D transform across the GPUs of one NVLink box (SURVEY.md section 8b
+ * "multi-GPU entry points ... additional exports", 8e; BASELINE config 5).  One process per GPU, the calling thread has
+ * its device current.  Rank g owns z-planes [g*D/P, (g+1)*D/P) of the dense (D, H, W) array: `in` is that [D/P][H][W] slab.
+ * The exchange is folded into the y pass's stores (peer memory over NVLink, CUDA IPC), ranks meet in flag barriers in peer
+ * memory; everything is enqueued on `stream` and on library-owned side streams that fork from and join it -- no host
+ * synchronisation, no collective library on the data path (csrc/slab.cu).  Power-of-two D, H <= 2048, divisible by nranks.
+ *
+ * Plan creation is collective.  The only thing the library cannot do itself is tell the ranks about each other: the host
+ * supplies an all-gather of small byte blobs (MPI_Allgather, ncclAllGather + copies, torch.distributed.all_gather, a pipe),
+ * called twice.  It returns 0 on success; `recv` holds nranks * bytes, rank r's blob at r * bytes.
+ */
+typedef struct b200fft_slab_s* b200fftSlabHandle;
+typedef int (*b200fftAllgatherFn)(void* ctx, const void* send, void* recv, size_t bytes);
+enum { B200FFT_SLAB_NATURAL = 1 };                 /* plan flag: also allocate what natural-layout output needs */
+enum { B200FFT_SLAB_NATURAL_OUT = 0,               /* out = [D/P][H][W], this rank's z-slab of fft3D's result (FFT.hs:150-173) */
+       B200FFT_SLAB_TRANSPOSED_OUT = 1 };          /* out = [D][H/P][W], this rank's ky rows for all kz (one exchange less) */
+int b200fftPlanSlab3d(b200fftSlabHandle* plan, int64_t d, int64_t h, int64_t w, int type, int rank, int nranks, int flags,
+                      b200fftAllgatherFn allgather, void* ctx);
+/* Collective: every rank calls it with the same arguments in the same order.  `scale` multiplies the result in the last
+ * pass (1/(D*H*W) for Mode Inverse, FFT.hs:155,172).  `in` is not written; `out` must not alias it. */
+int b200fftExecSlab(b200fftSlabHandle plan, const void* in_slab, void* out, int direction, double scale, int layout,
+                    b200fftStream stream);
+/* Natural layout: the result is assembled by the peers in a library-owned buffer and then copied to `out`; passing THIS
+ * buffer as `out` skips the copy (valid until the next exec on any rank has started). */
+int b200fftSlabNaturalBuffer(b200fftSlabHandle plan, void** ptr);
+/* Pipelining knobs (synchronises the device): the y pass goes in col_chunks column chunks x plane_chunks plane chunks on
+ * y_ctas CTAs (0 = one per tile); z of a chunk runs beside y of the next, x of a plane chunk beside y of the previous. */
+int b200fftSlabTune(b200fftSlabHandle plan, int plane_chunks, int col_chunks, int y_ctas);
+/* Collective by contract: no rank may destroy while another still executes. */
+int b200fftDestroySlab(b200fftSlabHandle plan);
 
 /*
  * Host-side mirror of the reference's public API for this path (FFT.hs:63-173 + PTX.hs +

@@ -49,6 +49,33 @@ for (d2, h2, w2) in ((64, 32, 48), (256, 1024, 64)):
         e3 = np.linalg.norm(back - full2[rank * dl2:(rank + 1) * dl2]) / np.linalg.norm(full2[rank * dl2:(rank + 1) * dl2])
         assert e1 < 1e-5 * 24 and e2 < 1e-5 * 24 and e3 < 2e-5 * 24, ("peer", rank, (d2, h2, w2), rep, e1, e2, e3)
     pf.close()
+# the same transform behind the C ABI (b200fftPlanSlab3d / b200fftExecSlab, csrc/slab.cu): pipeline, peer mappings and
+# barriers inside the library; default and chunked / SM-limited pipelines, both layouts, caller-owned outputs
+from accelerate_fft_b200.slab import SlabPlan
+for (d3, h3, w3) in ((64, 32, 48), (256, 1024, 64), (128, 256, 512)):
+    full3 = (rng.uniform(-1, 1, (d3, h3, w3)) + 1j * rng.uniform(-1, 1, (d3, h3, w3))).astype(np.complex64)
+    ref3 = np.fft.fftn(full3.astype(np.complex128))
+    dl3, hl3 = d3 // world, h3 // world
+    mine3 = torch.from_numpy(full3[rank * dl3:(rank + 1) * dl3]).cuda()
+    sp = SlabPlan(d3, h3, w3, torch.complex64, None)
+    for (cp, ck, yc) in ((1, 1, 0), (2, 2, 24), (4, 4, 48), (1, 3, 7)):
+        sp.tune(cp, ck, yc)
+        for rep in range(2):
+            tr = sp(af.Forward, mine3, transposed_out=True).cpu().numpy()
+            nat_d = sp(af.Forward, mine3)
+            nat = nat_d.cpu().numpy()
+            e1 = np.linalg.norm(nat - ref3[rank * dl3:(rank + 1) * dl3]) / np.linalg.norm(ref3[rank * dl3:(rank + 1) * dl3])
+            e2 = np.linalg.norm(tr - ref3[:, rank * hl3:(rank + 1) * hl3]) / np.linalg.norm(ref3[:, rank * hl3:(rank + 1) * hl3])
+            back = sp(af.Inverse, nat_d).cpu().numpy()
+            e3 = np.linalg.norm(back - full3[rank * dl3:(rank + 1) * dl3]) / np.linalg.norm(full3[rank * dl3:(rank + 1) * dl3])
+            assert e1 < 1e-5 * 26 and e2 < 1e-5 * 26 and e3 < 2e-5 * 26, ("cabi", rank, (d3, h3, w3), (cp, ck, yc), rep, e1, e2, e3)
+    sp.close()
+zd = (rng.uniform(-1, 1, (64, 32, 16)) + 1j * rng.uniform(-1, 1, (64, 32, 16)))
+spd = SlabPlan(64, 32, 16, torch.complex128, None)
+got = spd(af.Forward, torch.from_numpy(zd[rank * 64 // world:(rank + 1) * 64 // world]).cuda()).cpu().numpy()
+refd = np.fft.fftn(zd)[rank * 64 // world:(rank + 1) * 64 // world]
+assert np.linalg.norm(got - refd) / np.linalg.norm(refd) < 1e-13 * 15
+spd.close()
 # batched 1D sharded by rows: every rank transforms its contiguous share, results tile the full answer
 x = (rng.uniform(-1, 1, (64, 4096)) + 1j * rng.uniform(-1, 1, (64, 4096)))
 lo, hi = rank * 64 // world, (rank + 1) * 64 // world

@@ -84,6 +84,28 @@ def test_oracle_vs_exact_definition(oracle, n):
 
 
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+@pytest.mark.parametrize("n", [1, 2, 5, 16, 17, 60, 97, 128, 243, 1000, 1024, 4096])
+def test_two_oracles_agree(oracle, n, dtype):
+    """The restatement of the pure-Accelerate FFT (Adhoc.hs: split radix / mixed radix / Bluestein) against the restatement of
+    the reference's DEFINITION module (DFT.hs:42-59 + DFT/Roots.hs:26-51, O(n^2)), both in the working precision: two
+    different algorithms from two different reference modules must give the same transform -- sign, ordering and the
+    `Inverse` scale included.  The long-double definition sits between them."""
+    rng = np.random.default_rng(7000 + n)
+    x = rand_complex(rng, (2, n), dtype)
+    lg = max(1.0, np.log2(n))
+    eps = float(np.finfo(x.real.dtype).eps)
+    tol = max(bar(dtype, n), 2 * eps * np.sqrt(n) * lg)   # a left-to-right O(n^2) sum with roots from working-precision cos / sin
+    fwd, inv = oracle.dft(x), oracle.idft(x)
+    assert rel_l2(oracle.fft("Forward", x), fwd) <= tol
+    assert rel_l2(oracle.fft("Inverse", x), inv) <= tol
+    assert rel_l2(oracle.fft("Reverse", x), inv * x.real.dtype.type(n)) <= tol
+    ex = oracle.exact_dft(-1, x.astype(np.complex128))
+    assert rel_l2(fwd, ex) <= tol and rel_l2(oracle.fft("Forward", x), ex) <= tol
+    # idft . dft = id through the definition module alone
+    assert rel_l2(oracle.idft(fwd), x) <= 2 * tol
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 def test_oracle_baseline_shapes_vs_library(oracle, dtype):
     """cfg1 / cfg2 row lengths against pocketfft (stand-in for the reference's FFTW path)."""
     rng = np.random.default_rng(1001)
