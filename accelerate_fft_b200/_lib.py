@@ -100,7 +100,7 @@ def lib():
     L.b200fftPlanSlab3d.argtypes = [pvp, i64, i64, i64, i, i, i, i, ALLGATHER_FN, vp]
     L.b200fftExecSlab.argtypes = [vp, vp, vp, i, d, i, vp]
     L.b200fftSlabNaturalBuffer.argtypes = [vp, pvp]
-    L.b200fftSlabTune.argtypes = [vp, i, i, i]
+    L.b200fftSlabTune.argtypes = [vp, i, i, i, i]
     L.b200fftDestroySlab.argtypes = [vp]
     L.b200fftPeerAlloc.argtypes = [pvp, ctypes.c_size_t]
     L.b200fftPeerFree.argtypes = [vp]

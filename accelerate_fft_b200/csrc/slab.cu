@@ -8,7 +8,7 @@
 //   y pass   columns of the local planes; every ky row is stored straight into the memory of the rank that owns it
 //            (b200fftExecScatter over CUDA-IPC peer mappings: the all-to-all IS the pass's store, no pack, no collective
 //            library, no unpack) -- NVLink-bound, so it runs as a grid-stride loop on a FRACTION of the SMs
-//   z pass   columns along z of the received [D][H/P][W] block                 (HBM-bound, local); for the natural layout
+//   z pass   columns along z of the received [H/P][D][W] block                 (HBM-bound, local); for the natural layout
 //            it scatters back the same way into the z-slabs.
 // Pipelining: the y pass goes column chunk by column chunk (and, inside a chunk, plane chunk by plane chunk).  x of plane
 // chunk p+1 runs beside y of plane chunk p during the first column chunk; after a chunk's barrier its z pass runs beside the
@@ -63,9 +63,11 @@ struct b200fft_slab_s {
   unsigned magic = kSlabMagic;
   int type = 0, esz = 8, rank = 0, P = 1, natural = 0;
   int64_t d = 0, h = 0, w = 0, dl = 0, hl = 0;
-  int cp = 1, ck = 1, y_ctas = 0;             // plane chunks, column chunks, CTAs of the scatter pass (0 = all)
-  int64_t dlc = 0, wc = 0;
-  b200fftHandle px = nullptr, py = nullptr, pz = nullptr;
+  struct Pipe {                               // one pipelining configuration (and its plans) per output layout
+    int cp = 1, ck = 1, y_ctas = 0;           // plane chunks, column chunks, CTAs of the scatter pass (0 = one per tile)
+    int64_t dlc = 0, wc = 0;
+    b200fftHandle px = nullptr, py = nullptr, pz = nullptr;
+  } pipe[2];
   char *tmp = nullptr, *recv = nullptr, *back = nullptr;
   unsigned* flags = nullptr;
   std::vector<void*> recv_p, back_p, flag_p, opened;
@@ -77,7 +79,7 @@ struct b200fft_slab_s {
 
 namespace {
 
-void free_plans(b200fft_slab_s* s) {
+void free_plans(b200fft_slab_s::Pipe* s) {
   if (s->px) b200fftDestroy(s->px);
   if (s->py) b200fftDestroy(s->py);
   if (s->pz) b200fftDestroy(s->pz);
@@ -85,17 +87,19 @@ void free_plans(b200fft_slab_s* s) {
 }
 
 // (re)build the three local plans and the events for a chunking
-int build_plans(b200fft_slab_s* s, int cp, int ck) {
+int build_plans(b200fft_slab_s* s, int layout, int cp, int ck, int y_ctas) {
+  b200fft_slab_s::Pipe* q = &s->pipe[layout];
   if (cp < 1) cp = 1;
   if (ck < 1) ck = 1;
   while (cp > 1 && s->dl % cp) cp--;
   while (ck > 1 && (s->w % ck || (s->w / ck) % 16)) ck--;     // whole 128-byte runs per chunk
-  free_plans(s);
-  s->cp = cp; s->ck = ck; s->dlc = s->dl / cp; s->wc = s->w / ck;
-  int e = b200fftPlanMany1d(&s->px, s->w, s->dlc * s->h, s->type);
-  if (!e) e = b200fftPlanAxisView(&s->py, s->dlc, s->h, s->wc, s->h * s->w, s->w, s->type);
-  if (!e) e = b200fftPlanAxisView(&s->pz, s->hl, s->d, s->wc, s->w, s->hl * s->w, s->type);
-  if (e) { free_plans(s); return e; }
+  free_plans(q);
+  q->cp = cp; q->ck = ck; q->dlc = s->dl / cp; q->wc = s->w / ck; q->y_ctas = y_ctas < 0 ? 0 : y_ctas;
+  int e = b200fftPlanMany1d(&q->px, s->w, q->dlc * s->h, s->type);
+  if (!e) e = b200fftPlanAxisView(&q->py, q->dlc, s->h, q->wc, s->h * s->w, s->w, s->type);
+  // recv is [hl][D][W]: the z axis has row stride W (short-stride columns: the pipelined column kernel serves them)
+  if (!e) e = b200fftPlanAxisView(&q->pz, s->hl, s->d, q->wc, s->d * s->w, s->w, s->type);
+  if (e) { free_plans(q); return e; }
   auto grow = [](std::vector<cudaEvent_t>& v, size_t n) {
     while (v.size() < n) {
       cudaEvent_t ev;
@@ -177,20 +181,24 @@ int b200fftPlanSlab3d(b200fftSlabHandle* plan, int64_t d, int64_t h, int64_t w, 
     return fail(B200FFT_INTERNAL_ERROR);
   for (cudaEvent_t* ev : {&s->e_start, &s->e_b0, &s->e_sy, &s->e_sz, &s->e_sb})
     if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return fail(B200FFT_INTERNAL_ERROR);
-  // defaults measured on 8 x B200 (profiles/r02_slab_cabi.txt); b200fftSlabTune changes them
-  s->y_ctas = nranks > 1 ? env_int("B200FFT_SLAB_Y_CTAS", 0) : 0;
-  if ((e = build_plans(s, env_int("B200FFT_SLAB_PLANE_CHUNKS", 1), env_int("B200FFT_SLAB_COL_CHUNKS", 1)))) return fail(e);
+  // defaults measured on 2 and 8 x B200, 1024^3 c64 (profiles/r02_slab_cabi.txt); b200fftSlabTune changes them: 2 plane chunks x
+  // 2 column chunks with the scatter pass on 112 CTAs -- x of the second plane chunk and z of the first column chunk run beside
+  // the NVLink-bound y passes on the remaining SMs (8 GPUs: 2.10 -> 1.93 ms transposed-out, 3.11 -> 3.00 ms natural).
+  const bool big = nranks >= 2 && w >= 512 && s->dl >= 2;
+  if ((e = build_plans(s, B200FFT_SLAB_TRANSPOSED_OUT, big ? 2 : 1, big ? 2 : 1, big ? 112 : 0))) return fail(e);
+  if (s->natural && (e = build_plans(s, B200FFT_SLAB_NATURAL_OUT, big ? 2 : 1, big ? 2 : 1, big ? 112 : 0))) return fail(e);
   // nobody returns before every rank has mapped everything (a second exchange doubles as the barrier)
   if (allgather(ctx, blob, all.data(), sizeof blob) != 0) return fail(B200FFT_EXEC_FAILED);
   *plan = s;
   return B200FFT_SUCCESS;
 }
 
-int b200fftSlabTune(b200fftSlabHandle s, int plane_chunks, int col_chunks, int y_ctas) {
+int b200fftSlabTune(b200fftSlabHandle s, int layout, int plane_chunks, int col_chunks, int y_ctas) {
   if (!s || s->magic != kSlabMagic) return B200FFT_INVALID_PLAN;
+  if (layout != B200FFT_SLAB_TRANSPOSED_OUT && layout != B200FFT_SLAB_NATURAL_OUT) return B200FFT_INVALID_VALUE;
+  if (layout == B200FFT_SLAB_NATURAL_OUT && !s->natural) return B200FFT_NOT_SUPPORTED;
   cudaDeviceSynchronize();
-  s->y_ctas = y_ctas < 0 ? 0 : y_ctas;
-  return build_plans(s, plane_chunks, col_chunks);
+  return build_plans(s, layout, plane_chunks, col_chunks, y_ctas);
 }
 
 int b200fftSlabNaturalBuffer(b200fftSlabHandle s, void** ptr) {
@@ -208,7 +216,8 @@ int b200fftExecSlab(b200fftSlabHandle s, const void* in, void* out, int directio
   if (layout != B200FFT_SLAB_TRANSPOSED_OUT && layout != B200FFT_SLAB_NATURAL_OUT) return B200FFT_INVALID_VALUE;
   if (layout == B200FFT_SLAB_NATURAL_OUT && !s->natural) return B200FFT_NOT_SUPPORTED;
   cudaStream_t st = (cudaStream_t)stream_;
-  const int64_t esz = s->esz, plane = s->h * s->w * esz, rplane = s->hl * s->w * esz;
+  const b200fft_slab_s::Pipe* q = &s->pipe[layout];
+  const int64_t esz = s->esz, plane = s->h * s->w * esz, rplane = s->hl * s->w * esz, row = s->w * esz;
   int e = B200FFT_SUCCESS;
 #define CU(x) do { if ((x) != cudaSuccess) { cudaGetLastError(); return B200FFT_EXEC_FAILED; } } while (0)
 #define OK(x) do { if ((e = (x))) return e; } while (0)
@@ -222,33 +231,33 @@ int b200fftExecSlab(b200fftSlabHandle s, const void* in, void* out, int directio
   CU(cudaEventRecord(s->e_b0, s->sb));
   CU(cudaStreamWaitEvent(s->sy, s->e_b0, 0));
   // x: rows of the local planes, plane chunk by plane chunk, on the caller's stream
-  for (int p = 0; p < s->cp; p++) {
-    const int64_t off = (int64_t)p * s->dlc * plane;
-    OK(b200fftExec(s->px, (const char*)in + off, s->tmp + off, direction, st));
+  for (int p = 0; p < q->cp; p++) {
+    const int64_t off = (int64_t)p * q->dlc * plane;
+    OK(b200fftExec(q->px, (const char*)in + off, s->tmp + off, direction, st));
     CU(cudaEventRecord(s->e_x[p], st));
   }
   void* targets[kMaxRanks];
-  for (int c = 0; c < s->ck; c++) {
-    const int64_t coff = (int64_t)c * s->wc * esz;
-    // y: columns of the local planes, ky row -> its owner's recv[(rank*dl + z)][kyl][kx]
-    for (int p = 0; p < s->cp; p++) {
+  for (int c = 0; c < q->ck; c++) {
+    const int64_t coff = (int64_t)c * q->wc * esz;
+    // y: columns of the local planes, ky row -> its owner's recv[kyl][rank*dl + z][kx]
+    for (int p = 0; p < q->cp; p++) {
       if (c == 0) CU(cudaStreamWaitEvent(s->sy, s->e_x[p], 0));
-      const int64_t z0 = (int64_t)p * s->dlc;
-      for (int r = 0; r < s->P; r++) targets[r] = (char*)s->recv_p[r] + ((int64_t)s->rank * s->dl + z0) * rplane + coff;
-      OK(b200fftExecScatterOn(s->py, s->tmp + z0 * plane + coff, targets, s->P, s->hl * s->w, s->w, direction, 1.0, s->y_ctas, s->sy));
+      const int64_t z0 = (int64_t)p * q->dlc;
+      for (int r = 0; r < s->P; r++) targets[r] = (char*)s->recv_p[r] + ((int64_t)s->rank * s->dl + z0) * row + coff;
+      OK(b200fftExecScatterOn(q->py, s->tmp + z0 * plane + coff, targets, s->P, s->w, s->d * s->w, direction, 1.0, q->y_ctas, s->sy));
     }
     CU(cudaEventRecord(s->e_y[c], s->sy));
     CU(cudaStreamWaitEvent(s->sb, s->e_y[c], 0));
     OK(launch_barrier(s, s->sb));                     // this column chunk has landed everywhere
     CU(cudaEventRecord(s->e_b[c], s->sb));
     CU(cudaStreamWaitEvent(s->sz, s->e_b[c], 0));
-    // z: columns along z of recv[D][hl][W], chunk c of the columns
+    // z: columns along z of recv[hl][D][W], chunk c of the columns
     if (layout == B200FFT_SLAB_TRANSPOSED_OUT) {
-      OK(b200fftExecScaled(s->pz, s->recv + coff, (char*)out + coff, direction, scale, s->sz));
+      OK(b200fftExecScaled(q->pz, s->recv + coff, (char*)out + coff, direction, scale, s->sz));
     } else {
       // kz plane -> its owner's back[kzl][rank*hl + kyl][kx]
       for (int r = 0; r < s->P; r++) targets[r] = (char*)s->back_p[r] + (int64_t)s->rank * rplane + coff;
-      OK(b200fftExecScatterOn(s->pz, s->recv + coff, targets, s->P, s->w, s->h * s->w, direction, scale, 0, s->sz));
+      OK(b200fftExecScatterOn(q->pz, s->recv + coff, targets, s->P, s->w, s->h * s->w, direction, scale, 0, s->sz));
     }
   }
   CU(cudaEventRecord(s->e_sz, s->sz));
@@ -271,7 +280,8 @@ int b200fftDestroySlab(b200fftSlabHandle s) {
   if (!s || s->magic != kSlabMagic) return B200FFT_INVALID_PLAN;
   s->magic = 0;
   cudaDeviceSynchronize();
-  free_plans(s);
+  free_plans(&s->pipe[0]);
+  free_plans(&s->pipe[1]);
   for (void* q : s->opened) cudaIpcCloseMemHandle(q);
   for (void* q : {(void*)s->tmp, (void*)s->recv, (void*)s->back, (void*)s->flags})
     if (q) cudaFree(q);

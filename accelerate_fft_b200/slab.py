@@ -311,9 +311,24 @@ class SlabPlan:
                                          1 if natural else 0, self._cb, None), "b200fftPlanSlab3d")
         self.h = hnd
 
-    def tune(self, plane_chunks=1, col_chunks=1, y_ctas=0):
-        self.check(self.lib.b200fftSlabTune(self.h, plane_chunks, col_chunks, y_ctas), "b200fftSlabTune")
+    def tune(self, transposed_out, plane_chunks=1, col_chunks=1, y_ctas=0):
+        """Pipelining of one output layout: column chunks x plane chunks of the y pass, CTAs of the scatter pass."""
+        self.check(self.lib.b200fftSlabTune(self.h, self.TRANSPOSED_OUT if transposed_out else self.NATURAL_OUT, plane_chunks,
+                                            col_chunks, y_ctas), "b200fftSlabTune")
         return self
+
+    def natural_buffer(self):
+        """The library-owned buffer the peers assemble this rank's natural-layout result in, as a tensor (no copy).  Passing it
+        as `out` skips the final device copy; its content is valid until the next transform starts on any rank."""
+        if getattr(self, "_nat", None) is None:
+            torch, g = self.torch, self.geom
+            p = ctypes.c_void_p()
+            self.check(self.lib.b200fftSlabNaturalBuffer(self.h, ctypes.byref(p)), "b200fftSlabNaturalBuffer")
+            typestr = "<c8" if self.dtype == torch.complex64 else "<c16"
+            self._nat_holder = type("_Cai", (), {"__cuda_array_interface__": {"shape": (g.dl, g.h, g.w), "typestr": typestr,
+                                                                             "data": (p.value, False), "version": 2}})()
+            self._nat = torch.as_tensor(self._nat_holder, device="cuda")
+        return self._nat
 
     def __call__(self, mode, x_local, transposed_out=False, out=None):
         from . import FORWARD, INVERSE, Inverse, Forward
@@ -321,7 +336,8 @@ class SlabPlan:
         if tuple(x_local.shape) != (g.dl, g.h, g.w) or x_local.dtype != self.dtype or not x_local.is_cuda:
             raise ValueError("SlabPlan: expected this rank's (%d, %d, %d) %s z-slab on the device" % (g.dl, g.h, g.w, self.dtype))
         x_local = x_local.resolve_conj().resolve_neg().contiguous()
-        shape = (g.d, g.hl, g.w) if transposed_out else (g.dl, g.h, g.w)
+        # transposed-out: this rank's ky rows, each with all kz -- [H/P][D][W] (NOT the [D][H/P][W] of the Python-orchestrated classes)
+        shape = (g.hl, g.d, g.w) if transposed_out else (g.dl, g.h, g.w)
         if out is None:
             out = torch.empty(shape, dtype=self.dtype, device="cuda")
         sign = FORWARD if mode == Forward else INVERSE
@@ -333,6 +349,7 @@ class SlabPlan:
 
     def close(self):
         if self.h:
+            self._nat = None
             self.lib.b200fftDestroySlab(self.h)
             self.h = None
 

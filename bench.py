@@ -411,10 +411,12 @@ def slab_object(args, af, torch, dist, world, rank, local):
             ref = np.fft.fftn(folded)
             out["parity_oracle"] = "numpy fftn on the 16^3 fold (oracle unavailable: %r)" % (ex,)
 
-    def gather_bins(y, natural):
+    def gather_bins(y, natural, ky_major=False):
         """Y[64 kz, 64 ky, 64 kx] from the distributed result, summed over ranks (each bin lives on one rank)."""
         st = d // m
         bins = torch.zeros(m, m, m, dtype=torch.complex128, device="cuda")
+        if ky_major:     # the C ABI's transposed-out layout [hl][D][W]
+            y = y.transpose(0, 1)
         if natural:      # y: [dl][H][W], rank owns z in [rank*dl, (rank+1)*dl)
             for kz in range(m):
                 z = kz * st
@@ -450,18 +452,21 @@ def slab_object(args, af, torch, dist, world, rank, local):
     ms, par = {}, {}
     l0 = af.kernel_launches()
     try:
-        pf = S.PeerSlabFFT3D(d, h, w, torch.complex64, None)
-        for name, tr in (("p2p_transposed_out", True), ("p2p_natural_out", False)):
-            y = pf(af.Forward, x, transposed_out=tr)
-            got = gather_bins(y, natural=not tr)
+        # the C-ABI entry point (b200fftPlanSlab3d / b200fftExecSlab): pipeline, peer mappings and barriers in the library
+        sp = S.SlabPlan(d, h, w, torch.complex64, None)
+        outs = {True: torch.empty((geom.hl, d, w), dtype=torch.complex64, device="cuda"), False: sp.natural_buffer()}
+        for name, tr in (("cabi_transposed_out", True), ("cabi_natural_out", False)):
+            y = sp(af.Forward, x, transposed_out=tr, out=outs[tr])
+            got = gather_bins(y, natural=not tr, ky_major=tr)
             if rank == 0:
                 par[name] = rel(got, ref)
             del y
-            ms[name] = time_it(lambda: pf(af.Forward, x, transposed_out=tr))
-        pf.close()
-        del pf
+            ms[name] = time_it(lambda: sp(af.Forward, x, transposed_out=tr, out=outs[tr]))
+        del outs
+        sp.close()
+        del sp
     except Exception as ex:   # peer mappings unavailable (no P2P between the GPUs): the NCCL path stands
-        out["p2p_error"] = repr(ex)[:300]
+        out["cabi_error"] = repr(ex)[:300]
     torch.cuda.empty_cache()
     try:
         nf = S.SlabFFT3D(d, h, w, torch.complex64, None, chunks=4)
@@ -515,7 +520,7 @@ def slab_object(args, af, torch, dist, world, rank, local):
         "nvlink_out_gbs_per_gpu": {k: nvl_out * (1 if "transposed" in k else 2) / (v * 1e-3) / 1e9 for k, v in ms.items()},
         "nvlink_note": "bytes each GPU sends (one exchange transposed-out, two natural) / the WHOLE step time: a lower bound on the link rate during the exchange; measured peer copy 770 GB/s per direction (B200_PROFILING.md)",
         "hbm_frac_per_gpu": {k: 3 * 2 * slab_bytes / (v * 1e-3) / 1e9 / measured_peak()[0] for k, v in ms.items()},
-        "variants": "p2p_* = the y (and z) pass stores scattered straight into the owning rank's memory over NVLink peer mappings (b200fftExecScatter, no NCCL data path); nccl_* = pack + NCCL all-to-all (+ unpack), 4 chunks overlapped",
+        "variants": "cabi_* = b200fftExecSlab (C ABI, csrc/slab.cu): the y (and z) pass stores scattered straight into the owning rank's memory over NVLink peer mappings, z of a column chunk beside y of the next, flag barriers in peer memory, no NCCL on the data path; transposed-out = [H/P][D][W]; natural-out lands in the library-owned buffer (b200fftSlabNaturalBuffer; a caller-owned output adds one device copy of the slab).  nccl_* = pack + NCCL all-to-all (+ unpack), 4 chunks overlapped",
     })
     return out
 

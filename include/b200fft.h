@@ -138,7 +138,7 @@ typedef struct b200fft_slab_s* b200fftSlabHandle;
 typedef int (*b200fftAllgatherFn)(void* ctx, const void* send, void* recv, size_t bytes);
 enum { B200FFT_SLAB_NATURAL = 1 };                 /* plan flag: also allocate what natural-layout output needs */
 enum { B200FFT_SLAB_NATURAL_OUT = 0,               /* out = [D/P][H][W], this rank's z-slab of fft3D's result (FFT.hs:150-173) */
-       B200FFT_SLAB_TRANSPOSED_OUT = 1 };          /* out = [D][H/P][W], this rank's ky rows for all kz (one exchange less) */
+       B200FFT_SLAB_TRANSPOSED_OUT = 1 };          /* out = [H/P][D][W]: this rank's ky rows, each with all kz (one exchange less) */
 int b200fftPlanSlab3d(b200fftSlabHandle* plan, int64_t d, int64_t h, int64_t w, int type, int rank, int nranks, int flags,
                       b200fftAllgatherFn allgather, void* ctx);
 /* Collective: every rank calls it with the same arguments in the same order.  `scale` multiplies the result in the last
@@ -148,9 +148,10 @@ int b200fftExecSlab(b200fftSlabHandle plan, const void* in_slab, void* out, int 
 /* Natural layout: the result is assembled by the peers in a library-owned buffer and then copied to `out`; passing THIS
  * buffer as `out` skips the copy (valid until the next exec on any rank has started). */
 int b200fftSlabNaturalBuffer(b200fftSlabHandle plan, void** ptr);
-/* Pipelining knobs (synchronises the device): the y pass goes in col_chunks column chunks x plane_chunks plane chunks on
- * y_ctas CTAs (0 = one per tile); z of a chunk runs beside y of the next, x of a plane chunk beside y of the previous. */
-int b200fftSlabTune(b200fftSlabHandle plan, int plane_chunks, int col_chunks, int y_ctas);
+/* Pipelining knobs of one output layout (synchronises the device): the y pass goes in col_chunks column chunks x
+ * plane_chunks plane chunks on y_ctas CTAs (0 = one per tile); z of a chunk runs beside y of the next, x of a plane chunk
+ * beside y of the previous.  The defaults are the measured optimum on 8 x B200. */
+int b200fftSlabTune(b200fftSlabHandle plan, int layout, int plane_chunks, int col_chunks, int y_ctas);
 /* Collective by contract: no rank may destroy while another still executes. */
 int b200fftDestroySlab(b200fftSlabHandle plan);
 

@@ -58,11 +58,13 @@ for (d3, h3, w3) in ((64, 32, 48), (256, 1024, 64), (128, 256, 512)):
     dl3, hl3 = d3 // world, h3 // world
     mine3 = torch.from_numpy(full3[rank * dl3:(rank + 1) * dl3]).cuda()
     sp = SlabPlan(d3, h3, w3, torch.complex64, None)
-    for (cp, ck, yc) in ((1, 1, 0), (2, 2, 24), (4, 4, 48), (1, 3, 7)):
-        sp.tune(cp, ck, yc)
+    for (cp, ck, yc) in ((None, None, None), (1, 1, 0), (2, 2, 24), (4, 4, 48), (1, 3, 7)):
+        if cp is not None:     # (the first round runs the library's defaults)
+            sp.tune(True, cp, ck, yc)
+            sp.tune(False, cp, ck, yc)
         for rep in range(2):
-            tr = sp(af.Forward, mine3, transposed_out=True).cpu().numpy()
-            nat_d = sp(af.Forward, mine3)
+            tr = sp(af.Forward, mine3, transposed_out=True).cpu().numpy().transpose(1, 0, 2)     # [hl][D][W] -> [D][hl][W]
+            nat_d = sp(af.Forward, mine3) if rep == 0 else sp(af.Forward, mine3, out=sp.natural_buffer()).clone()
             nat = nat_d.cpu().numpy()
             e1 = np.linalg.norm(nat - ref3[rank * dl3:(rank + 1) * dl3]) / np.linalg.norm(ref3[rank * dl3:(rank + 1) * dl3])
             e2 = np.linalg.norm(tr - ref3[:, rank * hl3:(rank + 1) * hl3]) / np.linalg.norm(ref3[:, rank * hl3:(rank + 1) * hl3])
