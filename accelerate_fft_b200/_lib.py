@@ -24,7 +24,7 @@ EXPORTS = [
     "accfft_set_fused_inverse", "accfft_plan_cache_size", "accfft_plan_cache_clear",
     "b200fftPlanAxis", "b200fftSlabPack", "b200fftSlabUnpack", "b200fftTrimScratch",
     "b200fftExecShifted", "accfft_centre", "accfft_shift", "accfft_fft_centred",
-    "b200fftExecScatterOn", "b200fftPlanAxisView",
+    "b200fftExecScatterOn", "b200fftPlanAxisView", "b200fftHasExperimental",
     "b200fftPlanSlab3d", "b200fftExecSlab", "b200fftSlabNaturalBuffer", "b200fftSlabTune", "b200fftDestroySlab",
     "b200fftExecScatter", "b200fftPeerAlloc", "b200fftPeerFree", "b200fftPeerExport", "b200fftPeerOpen", "b200fftPeerClose",
 ]

@@ -10,10 +10,16 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler has injected itself
+
+#include <atomic>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <vector>
+
+extern char** environ;
 
 #include "../../include/b200fft.h"
 #include "generic.h"
@@ -27,13 +33,26 @@ int fft_direction(int mode) { return mode == Forward ? B200FFT_FORWARD : B200FFT
 
 // PTX/Plans.hs:40-44: the reference keys on (context pointer, hash of (shape,type)); we key on the
 // full tuple so two shapes can never share a plan through a hash collision.
-using Key = std::tuple<void*, int, int64_t, int64_t, int64_t>;  // ctx, type, d, h, w
+// The planner's developer switches are environment variables (B200FFT_*) read at plan creation: their fingerprint is part
+// of the key, so a plan made under one setting is never handed out under another.
+using Key = std::tuple<void*, int, int64_t, int64_t, int64_t, uint64_t>;  // ctx, type, d, h, w, planner-environment fingerprint
 
 struct Plans {
   std::mutex lock;
   std::map<Key, b200fftHandle> plans;
   int (*create)(b200fftHandle*, int64_t, int64_t, int64_t, int);
+  const char* name;   // the reference's ForeignAcc name for this cache (PTX.hs:59-70): the NVTX range of every exec
 };
+
+uint64_t planner_env_fingerprint() {
+  uint64_t h = 1469598103934665603ull;   // FNV-1a over every "B200FFT_*=value" string
+  for (char** e = environ; e && *e; e++) {
+    if (strncmp(*e, "B200FFT_", 8) != 0) continue;
+    for (const char* c = *e; *c; c++) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
+    h ^= 0xff; h *= 1099511628211ull;
+  }
+  return h;
+}
 
 int mk1d(b200fftHandle* h, int64_t, int64_t, int64_t n, int t) { return b200fftPlan1d(h, n, t, 1); }                   // PTX.hs:141
 int mk2d(b200fftHandle* h, int64_t, int64_t hh, int64_t w, int t) { return b200fftPlan2d(h, hh, w, t); }                // PTX.hs:148
@@ -42,23 +61,46 @@ int mk2many(b200fftHandle* h, int64_t, int64_t hh, int64_t w, int t) { return b2
 int mk3many(b200fftHandle* h, int64_t d, int64_t hh, int64_t w, int t) { return b200fftPlanMany1d(h, w, d * hh, t); }   // PTX.hs:169
 
 // PTX.hs:137-170: five global caches
-Plans fft1D_plans{{}, {}, mk1d}, fft2D_plans{{}, {}, mk2d}, fft3D_plans{{}, {}, mk3d}, fft2DMany_plans{{}, {}, mk2many},
-    fft3DMany_plans{{}, {}, mk3many};
+Plans fft1D_plans{{}, {}, mk1d, "cuda.fft1d"}, fft2D_plans{{}, {}, mk2d, "cuda.fft2d"}, fft3D_plans{{}, {}, mk3d, "cuda.fft3d"},
+    fft2DMany_plans{{}, {}, mk2many, "cuda.fft2.many"}, fft3DMany_plans{{}, {}, mk3many, "cuda.fft3.many"};
 Plans* all_caches[] = {&fft1D_plans, &fft2D_plans, &fft3D_plans, &fft2DMany_plans, &fft3DMany_plans};
 
-bool g_fused_inverse = false;
+// how `run` normalises Mode Inverse; a process-wide developer switch read once per call (atomic: GHC calls from many threads)
+std::atomic<int> g_fused_inverse{0};
+
+template <typename F>
+F driver_entry(const char* name) {
+  // Driver entry points are fetched through the runtime so the library carries no link-time dependency on libcuda.so
+  // (it must load, and report NO_DEVICE, on a box without a driver).
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qr) != cudaSuccess) { cudaGetLastError(); fn = nullptr; }
+  return (F)fn;
+}
+
+// PTX/Plans.hs:78-80: the reference drops a cache entry when its CUDA context dies (a finaliser on the context's Lifetime).
+// There is no such hook below the FFI, so every insertion sweeps the cache instead: entries whose context no longer answers
+// are destroyed (their device memory went with the context; the handle's host side is what is left to free).
+void evict_dead_contexts(Plans& ps, void* current) {
+  typedef CUresult (*api_version_t)(CUcontext, unsigned int*);
+  static api_version_t api_version = driver_entry<api_version_t>("cuCtxGetApiVersion");
+  if (!api_version) return;
+  for (auto it = ps.plans.begin(); it != ps.plans.end();) {
+    void* ctx = std::get<0>(it->first);
+    unsigned int v = 0;
+    if (ctx != current && api_version((CUcontext)ctx, &v) != CUDA_SUCCESS) {
+      b200fftDestroy(it->second);
+      it = ps.plans.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
 
 // PTX/Plans.hs:66-86 withPlan: look up / create under the lock, return the handle, run outside it
 int with_plan(Plans& ps, int64_t d, int64_t h, int64_t w, int type, b200fftHandle* out) {
-  // The driver entry point is fetched through the runtime so the library carries no link-time
-  // dependency on libcuda.so (it must load, and report NO_DEVICE, on a box without a driver).
   typedef CUresult (*ctx_get_t)(CUcontext*);
-  static ctx_get_t ctx_get = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &fn, cudaEnableDefault, &qr) != cudaSuccess) { cudaGetLastError(); fn = nullptr; }
-    return (ctx_get_t)fn;
-  }();
+  static ctx_get_t ctx_get = driver_entry<ctx_get_t>("cuCtxGetCurrent");
   if (!ctx_get) return B200FFT_NO_DEVICE;
   CUcontext ctx = nullptr;
   if (ctx_get(&ctx) != CUDA_SUCCESS || ctx == nullptr) {
@@ -66,13 +108,15 @@ int with_plan(Plans& ps, int64_t d, int64_t h, int64_t w, int type, b200fftHandl
     if (cudaFree(0) != cudaSuccess) { cudaGetLastError(); return B200FFT_NO_DEVICE; }
     if (ctx_get(&ctx) != CUDA_SUCCESS || ctx == nullptr) return B200FFT_NO_DEVICE;
   }
+  const uint64_t env = planner_env_fingerprint();
   std::lock_guard<std::mutex> g(ps.lock);
-  Key key{(void*)ctx, type, d, h, w};
+  Key key{(void*)ctx, type, d, h, w, env};
   auto it = ps.plans.find(key);
   if (it != ps.plans.end()) { *out = it->second; return 0; }
   b200fftHandle hnd = nullptr;
   int e = ps.create(&hnd, d, h, w, type);
   if (e) return e;
+  evict_dead_contexts(ps, (void*)ctx);
   ps.plans.emplace(key, hnd);
   *out = hnd;
   return 0;
@@ -92,9 +136,11 @@ int run(Plans& ps, int mode, int64_t d, int64_t h, int64_t w, int type, double s
         b200fftStream stream) {
   if (mode < Forward || mode > Inverse) return B200FFT_INVALID_VALUE;
   if (type != B200FFT_C2C && type != B200FFT_Z2Z) return B200FFT_INVALID_TYPE;
+  struct Range { Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } } range(ps.name);
   b200fftHandle hnd = nullptr;
   if (int e = with_plan(ps, d, h, w, type, &hnd)) return e;
-  if (mode == Inverse && g_fused_inverse) return b200fftExecScaled(hnd, in, out, fft_direction(mode), 1.0 / scale, stream);
+  if (mode == Inverse && g_fused_inverse.load(std::memory_order_relaxed))
+    return b200fftExecScaled(hnd, in, out, fft_direction(mode), 1.0 / scale, stream);
   if (int e = b200fftExec(hnd, in, out, fft_direction(mode), stream)) return e;
   if (mode == Inverse) {  // case mode of Inverse -> A.map (/scale) (go arr)
     const long long n = (long long)d * h * w;
@@ -105,6 +151,32 @@ int run(Plans& ps, int mode, int64_t d, int64_t h, int64_t w, int type, double s
     if (cudaGetLastError() != cudaSuccess) return B200FFT_EXEC_FAILED;
   }
   return 0;
+}
+
+// stream sets of accfft_run_host_seq, kept per device between calls
+struct StreamSet { int dev; cudaStream_t st[3]; };
+std::mutex g_ss_lock;
+std::vector<StreamSet> g_ss_free;
+bool take_streams(StreamSet* out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+  {
+    std::lock_guard<std::mutex> g(g_ss_lock);
+    for (size_t i = 0; i < g_ss_free.size(); i++)
+      if (g_ss_free[i].dev == dev) { *out = g_ss_free[i]; g_ss_free.erase(g_ss_free.begin() + i); return true; }
+  }
+  out->dev = dev;
+  for (int s = 0; s < 3; s++)
+    if (cudaStreamCreateWithFlags(&out->st[s], cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      for (int q = 0; q < s; q++) cudaStreamDestroy(out->st[q]);
+      return false;
+    }
+  return true;
+}
+void give_streams(const StreamSet& ss) {
+  std::lock_guard<std::mutex> g(g_ss_lock);
+  g_ss_free.push_back(ss);
 }
 
 }  // namespace
@@ -268,11 +340,13 @@ int accfft_run_host_seq(int kind, const int* modes, int nmodes, int rank, const 
   const int nslot = nchunks > 1 ? NSLOT : 1;
   const size_t chunk_bytes = (size_t)rows_per_chunk * w * esz;
 
-  cudaStream_t st[NSLOT] = {nullptr, nullptr, nullptr};
+  // the three copy / compute streams are kept between calls (a call takes a set from the free list and returns it)
+  StreamSet ss;
+  if (!take_streams(&ss)) return B200FFT_ALLOC_FAILED;
+  cudaStream_t* st = ss.st;
   void *a[NSLOT] = {nullptr, nullptr, nullptr}, *b[NSLOT] = {nullptr, nullptr, nullptr};
   int e = 0;
   for (int s = 0; s < nslot && !e; s++) {
-    if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess) { e = B200FFT_ALLOC_FAILED; break; }
     if (b200fft::pool_alloc(&a[s], chunk_bytes, st[s]) != cudaSuccess || b200fft::pool_alloc(&b[s], chunk_bytes, st[s]) != cudaSuccess)
       e = B200FFT_ALLOC_FAILED;
   }
@@ -293,12 +367,11 @@ int accfft_run_host_seq(int kind, const int* modes, int nmodes, int rank, const 
     if (cudaMemcpyAsync((char*)h_out + off, res, cb, cudaMemcpyDeviceToHost, st[s]) != cudaSuccess) e = B200FFT_EXEC_FAILED;
   }
   for (int s = 0; s < nslot; s++) {
-    if (!st[s]) continue;
     if (a[s]) cudaFreeAsync(a[s], st[s]);
     if (b[s]) cudaFreeAsync(b[s], st[s]);
     if (cudaStreamSynchronize(st[s]) != cudaSuccess && !e) e = B200FFT_EXEC_FAILED;
-    cudaStreamDestroy(st[s]);
   }
+  give_streams(ss);
   if (e) cudaGetLastError();
   return e;
 }

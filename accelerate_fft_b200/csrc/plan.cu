@@ -217,6 +217,7 @@ using namespace b200fft;
 
 struct b200fft_plan_s {
   unsigned magic = 0xB200FF7u;
+  bool upload_failed = false;   // a twiddle table could not be allocated / copied: the plan must not be handed out
   int is_double = 0;
   int rank = 0;
   long long dims[3] = {1, 1, 1};
@@ -241,9 +242,9 @@ template <typename T>
 static void* upload(b200fft_plan_s* p, const std::vector<T>& h) {
   void* d = nullptr;
   if (h.empty()) return nullptr;
-  if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
-  cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  if (cudaMalloc(&d, h.size() * sizeof(T)) != cudaSuccess) { cudaGetLastError(); p->upload_failed = true; return nullptr; }
   p->dev_allocs.push_back(d);
+  if (cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); p->upload_failed = true; }
   return d;
 }
 
@@ -1070,9 +1071,9 @@ struct Builder {
     Pass ps;
     int e = plan_generic_axis(p->is_double, O, N, I, &ps.gp, [&](const void* h, size_t bytes) -> void* {
       void* d = nullptr;
-      if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
-      cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice);
+      if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); p->upload_failed = true; return nullptr; }
       p->dev_allocs.push_back(d);
+      if (cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); p->upload_failed = true; }
       return d;
     });
     if (e) { err = e; return; }
@@ -1186,6 +1187,7 @@ static int set_func_attrs(b200fft_plan_s* p) {
 
 static int finish_plan(b200fft_plan_s* p, Builder& b, b200fftHandle* out) {
   if (!b.err) b.route();
+  if (!b.err && p->upload_failed) b.err = B200FFT_ALLOC_FAILED;
   if (!b.err) b.err = set_func_attrs(p);
   if (b.err) {
     for (auto& ps : p->passes) destroy_generic(&ps.gp);
@@ -1643,6 +1645,14 @@ int b200fftTrimScratch(void) {
   for (auto& kv : g_pools) cudaMemPoolTrimTo(kv.second, 0);
   cudaGetLastError();
   return B200FFT_SUCCESS;
+}
+
+int b200fftHasExperimental(void) {
+#ifdef B200FFT_EXPERIMENTAL
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 size_t b200fftScratchBytes(b200fftHandle p) { return p ? p->scratch_bytes + p->extra_bytes + p->band_bytes : 0; }

@@ -89,6 +89,7 @@ int b200fftTrimScratch(void);
 size_t b200fftScratchBytes(b200fftHandle plan);      /* stream-ordered scratch one exec allocates */
 int b200fftNumPasses(b200fftHandle plan);            /* kernel launches (= HBM passes) per exec */
 int64_t b200fftKernelLaunches(void);                 /* process-wide count of kernels launched */
+int b200fftHasExperimental(void);                    /* 1 if built with B200FFT_EXPERIMENTAL=1 (opt-in kernels that measured slower) */
 /* fills `buf` with a one-line-per-pass description of the plan; returns bytes written */
 int b200fftDescribe(b200fftHandle plan, char* buf, int buflen);
 
