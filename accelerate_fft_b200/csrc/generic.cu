@@ -11,6 +11,7 @@
 
 #include "../../include/b200fft.h"
 #include "cplx.cuh"
+#include "bluestein_kernel.cuh"
 
 namespace b200fft {
 
@@ -570,6 +571,40 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
     gp->filt = up(f32.data(), f32.size() * sizeof(float));
   }
   if (!gp->chirp || !gp->filt) return B200FFT_ALLOC_FAILED;
+  const BluesteinEntry* be = (I == 1 && !(getenv("B200FFT_BLUESTEIN_FUSED") && atoi(getenv("B200FFT_BLUESTEIN_FUSED")) == 0))
+                                 ? find_bluestein(is_double, M) : nullptr;
+  if (be) {
+    // contiguous lines: pack, both transforms, filter and unpack in one launch, the lines never leave the SM
+    std::vector<double> ht(2 * (size_t)(be->tw_len > 0 ? be->tw_len : 1), 0.0);
+    {
+      const long double two_pi = 6.283185307179586476925286766559005768L;
+      size_t off = 0;
+      long long Ns = be->rad[0];
+      for (int s = 1; s < be->S; s++) {     // stage s >= 1: entry [(r-1)*Ns + k] = w_{Ns R}^(r k)  (as plan.cu make_stage_twiddles)
+        const int R = be->rad[s];
+        for (int r = 1; r < R; r++)
+          for (long long kk = 0; kk < Ns; kk++) {
+            const long double a = two_pi * (long double)((r * kk) % (Ns * R)) / (long double)(Ns * R);
+            ht[2 * (off + (size_t)(r - 1) * Ns + kk)] = (double)cosl(a);
+            ht[2 * (off + (size_t)(r - 1) * Ns + kk) + 1] = (double)(-sinl(a));
+          }
+        off += (size_t)(R - 1) * Ns;
+        Ns *= R;
+      }
+    }
+    if (is_double) gp->fused_tw = up(ht.data(), ht.size() * sizeof(double));
+    else { std::vector<float> t32(ht.begin(), ht.end()); gp->fused_tw = up(t32.data(), t32.size() * sizeof(float)); }
+    if (!gp->fused_tw) return B200FFT_ALLOC_FAILED;
+    gp->fused = be->func; gp->fused_tl = be->TL; gp->fused_threads = be->threads; gp->fused_smem = be->smem;
+    if (be->smem > 48 * 1024 && cudaFuncSetAttribute(be->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)be->smem) != cudaSuccess) {
+      cudaGetLastError();
+      return B200FFT_INTERNAL_ERROR;
+    }
+    gp->workspace_bytes = 0;
+    snprintf(gp->desc, sizeof gp->desc, "bluestein N=%lld on M=%lld in one launch: chirp, FFT, filter, IFFT, chirp on chip; TL=%d threads=%d smem=%zu (O=%lld)",
+             N, M, be->TL, be->threads, be->smem, O);
+    return 0;
+  }
   e = b200fftPlanMany1d(&gp->sub, M, chunk, is_double ? B200FFT_Z2Z : B200FFT_C2C);
   if (e) return e;
   snprintf(gp->desc, sizeof gp->desc, "bluestein N=%lld M=%lld chunk=%lld lines (%d sub-passes x2 + 3 pointwise) (O=%lld I=%lld)", N, M,
@@ -612,6 +647,16 @@ static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst,
     mixed_radix_kernel<C><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
     *nl += 1;
     return cudaGetLastError();
+  }
+  if (gp.fused) {
+    const C* chirp = (const C*)gp.chirp; const C* filt = (const C*)gp.filt; const C* tws = (const C*)gp.fused_tw;
+    int n = (int)gp.N, swap_in = inverse & 1, swap_out = (inverse >> 1) & 1;
+    long long lines = gp.lines;
+    T sc = (T)scale;
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&chirp, (void*)&filt, (void*)&tws, &n, &lines, &swap_in, &swap_out, &sc};
+    const long long tiles = (gp.lines + gp.fused_tl - 1) / gp.fused_tl;
+    *nl += 1;
+    return cudaLaunchKernel(gp.fused, dim3((unsigned)tiles), dim3(gp.fused_threads), args, gp.fused_smem, stream);
   }
   const long long M = gp.M, N = gp.N;
   C* A = (C*)workspace;

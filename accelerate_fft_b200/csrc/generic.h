@@ -23,6 +23,10 @@ struct GenericPass {
   void* chirp = nullptr;          // device, N entries: exp(-i pi n^2/N)
   void* filt = nullptr;           // device, M entries: FFT_M(wrapped conj chirp) / M
   b200fft_plan_s* sub = nullptr;  // rows of length M, batch chunk_lines
+  const void* fused = nullptr;    // contiguous lines, M <= 4096: the whole chain in one launch (bluestein_kernel.cuh)
+  void* fused_tw = nullptr;       // device: stage twiddles of the M-point engine
+  int fused_tl = 0, fused_threads = 0;
+  size_t fused_smem = 0;
   // mixed radix
   int nstages = 0;
   int radix[40] = {0};

@@ -33,12 +33,14 @@ void register_pipe(void (*add)(const KernelEntry&)) {
   // (landing buffer in 2 / 8 parts instead of 4: 88.1 % / 74.5 % against 90.2 % on [64][1024][1024])
   REG_PIPE_TW(1, float, 1024, 32, 8, 1, 32, 32);
   REG_PIPE(2, float, 1024, 32, 8, 1, 32, 32);
+#ifdef B200FFT_EXPERIMENTAL   // opt-in, measured slower than the default plans (they ride on the cluster column kernels' planner path)
   REG_PIPE(4, float, 1024, 32, 8, 1, 32, 32);
   REG_PIPE(8, float, 1024, 32, 8, 1, 32, 32);            // cfg3's column axis
   REG_PIPE(16, float, 1024, 32, 8, 1, 32, 32);
   // contiguous rows: one 64 KB line per tile
   REG_PIPE_ROWS(float, 8192, 32, 1, 1, 32, 16, 16);
   REG_PIPE_ROWS(double, 4096, 16, 1, 1, 16, 16, 16);
+#endif
   // c64 N=512: 16 columns (128 B runs)
   REG_PIPE(1, float, 512, 32, 16, 1, 32, 16);
   REG_PIPE_TW(1, float, 512, 32, 16, 1, 32, 16);
@@ -50,8 +52,10 @@ void register_pipe(void (*add)(const KernelEntry&)) {
   REG_PIPE(1, double, 512, 16, 8, 1, 16, 16, 2);
   REG_PIPE_TW(1, double, 512, 16, 8, 1, 16, 16, 2);
   REG_PIPE(2, double, 512, 16, 8, 1, 16, 16, 2);
+#ifdef B200FFT_EXPERIMENTAL
   REG_PIPE(4, double, 512, 16, 8, 1, 16, 16, 2);
   REG_PIPE(8, double, 512, 16, 8, 1, 16, 16, 2);
   REG_PIPE(16, double, 512, 16, 8, 1, 16, 16, 2);
+#endif
 }
 }  // namespace b200fft
