@@ -363,6 +363,10 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
                  const cpx_t<typename K::real>* __restrict__ tw_hi, typename K::real scale) {
   using C = cpx_t<typename K::real>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // programmatic dependent launch (plan.cu): let the next kernel on the stream be scheduled as this one drains, and do not
+  // touch global memory before the previous kernel has completed and flushed (both are no-ops under an ordinary launch)
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if constexpr (!LLF && !SLF && !TW4 && !PRE2 && K::SMALL_ROWS) {
     if (g.ils == K::N && g.ols == K::N && g.ins == 1 && g.ons == 1 && g.npeers == 0) {   // CTA-uniform
       fft_small_rows_tile<K>(g, blockIdx.x, in, out, scale, reinterpret_cast<C*>(smem_raw));

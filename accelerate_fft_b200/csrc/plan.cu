@@ -202,6 +202,7 @@ struct Pass {
   // PK_BAND: two phases fused through L2 (band_kernel.cuh); tws / twsB = stage twiddles, tw_lo / tw_hi = inner four-step table
   const BandEntry* bz = nullptr;
   BandParams bp{};
+  size_t slot_bytes = 0, counter_bytes = 0, counter_off = 0;   // fused / band passes: their share of the plan's band scratch
   void* otw_lo = nullptr;          // outer four-step table (OUTER kernels)
   void* otw_hi = nullptr;
   unsigned long long tm_dims[4] = {1, 1, 1, 1};     // tensor map of phase A's input: extents (elements of the real type) ...
@@ -227,7 +228,8 @@ struct b200fft_plan_s {
   std::vector<void*> dev_allocs;
   size_t scratch_bytes = 0;   // main scratch (same size as the array) if any pass uses BUF_SCRATCH
   size_t extra_bytes = 0;     // bluestein workspace
-  size_t band_bytes = 0;      // fused passes: two L2-resident band slots + the ticket / progress counters
+  size_t band_bytes = 0;      // fused / band passes: the L2-resident slots + every such pass's progress counters
+  size_t band_slot_bytes = 0; // ... of which the slots (the counters follow)
   bool no_shift = false;      // built by a whole-transform builder that does not mark the axes' last passes (b200fftExecShifted)
   // Plans holding a PK_BAND pass need 16-byte aligned buffers (TMA) and cannot rotate their stores: the same transform
   // planned without band passes serves misaligned buffers and b200fftExecShifted.
@@ -518,8 +520,8 @@ struct Builder {
     ps.ntiles = total;
     ps.mid_in_dst = mid_in_dst;
     ps.inplace_ok = inplace_ok;
-    const size_t need = counters_bytes(fp.nbands) + (mid_in_dst ? 0 : (size_t)fp.nslots * fp.slot_elems * esize(p));
-    if (need > p->band_bytes) p->band_bytes = need;
+    ps.counter_bytes = counters_bytes(fp.nbands);
+    ps.slot_bytes = mid_in_dst ? 0 : (size_t)fp.nslots * fp.slot_elems * esize(p);
     char buf[384];
     snprintf(buf, sizeof buf,
              "%s: fused A[N=%d %s%s E=%d TL=%d] -> %s -> B[N=%d %s E=%d TL=%d] threads=%d smem=%zu bands=%d tiles/band=%lld+%lld",
@@ -702,8 +704,8 @@ struct Builder {
     ps.tm_box[0] = 2u * (unsigned)bz->TLA; ps.tm_box[1] = 1; ps.tm_box[2] = (unsigned)N1; ps.tm_box[3] = 1;
     ps.inplace_ok = true;
     ps.ntiles = nbands * (nA + nB);
-    const size_t need = counters_bytes(bp.nbands) + (size_t)bp.nslots * (size_t)bp.slot_elems * esize(p);
-    if (need > p->band_bytes) p->band_bytes = need;
+    ps.counter_bytes = counters_bytes(bp.nbands);
+    ps.slot_bytes = (size_t)bp.nslots * (size_t)bp.slot_elems * esize(p);
     char buf[384];
     snprintf(buf, sizeof buf,
              "4step-strided: band A[N=%d col+tw TL=%d] -> L2 slots -> B[N=%d col%s TL=%d] | persistent TMA-fed, threads=%d smem=%zu bands=%lld x %lld cols "
@@ -767,8 +769,8 @@ struct Builder {
     ps.tm_box[0] = 2u * (unsigned)TLA; ps.tm_box[1] = (unsigned)N1; ps.tm_box[2] = 1; ps.tm_box[3] = 1;
     ps.inplace_ok = false;
     ps.ntiles = nbands * (nA + nB);
-    const size_t need = counters_bytes(bp.nbands) + (size_t)bp.nslots * (size_t)bp.slot_elems * esize(p);
-    if (need > p->band_bytes) p->band_bytes = need;
+    ps.counter_bytes = counters_bytes(bp.nbands);
+    ps.slot_bytes = (size_t)bp.nslots * (size_t)bp.slot_elems * esize(p);
     char buf[384];
     snprintf(buf, sizeof buf,
              "4step-rows: band A[N=%d col+tw TL=%d] -> L2 slots -> B[N=%d trans TL=%d] | persistent TMA-fed, threads=%d smem=%zu bands=%lld x %lld rows "
@@ -794,10 +796,8 @@ struct Builder {
       const long long Nout = N / M;
       if (Nout < 4096 || Nout > 16384) continue;
       const size_t n0 = p->passes.size();
-      const size_t bb0 = p->band_bytes;
       if (try_band_strided(O, Nout, M, true, N, 0) && try_band_rows(O, Nout, M)) return true;
       p->passes.resize(n0);
-      p->band_bytes = bb0;
     }
     return false;
   }
@@ -1105,6 +1105,17 @@ struct Builder {
     bool uses_scratch = false;
     for (auto& ps : P) uses_scratch |= (ps.src == BUF_SCRATCH || ps.dst == BUF_SCRATCH);
     p->scratch_bytes = uses_scratch ? (size_t)p->total * esize(p) : 0;
+    // band scratch: the slots (shared by the passes, which run one after the other) then every pass's own counters, so that
+    // all counters can be cleared up front and no memset sits between two kernels of an exec
+    size_t slots = 0, counters = 0;
+    for (auto& ps : P) {
+      if (ps.slot_bytes > slots) slots = ps.slot_bytes;
+      ps.counter_off = counters;
+      counters += ps.counter_bytes;
+    }
+    slots = (slots + 255) / 256 * 256;
+    p->band_slot_bytes = slots;
+    p->band_bytes = counters ? slots + counters : 0;
   }
 };
 
@@ -1369,6 +1380,8 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
   const int inverse = direction == B200FFT_INVERSE;
   int status = B200FFT_SUCCESS;
   const size_t np = p->passes.size();
+  if (band && cudaMemsetAsync((char*)band + p->band_slot_bytes, 0, p->band_bytes - p->band_slot_bytes, stream) != cudaSuccess)
+    status = B200FFT_EXEC_FAILED;
   for (size_t i = 0; i < np && status == B200FFT_SUCCESS; i++) {
     const Pass& ps = p->passes[i];
     const void* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : scratch;
@@ -1424,7 +1437,21 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
         g.ntl = ps.ring_ntl;
         ce = cudaLaunchKernel(ps.ring->func, dim3((unsigned)ps.ring_grid), dim3(ps.ring->threads), args, ps.ring->smem, stream);
       } else {
-        ce = cudaLaunchKernel(ps.k->func, dim3((unsigned)ps.ntiles), dim3(ps.k->threads), args, ps.k->smem, stream);
+        // Programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream drains (its CTAs
+        // take the SMs the predecessor's last wave leaves idle and sit in griddepcontrol.wait until it has completed and
+        // flushed), so back-to-back transforms lose the launch latency and the scheduling ramp between them.  The lines
+        // kernel touches no global memory before that wait, so stream order is what it always was.
+        static const bool pdl = !(getenv("B200FFT_PDL") && atoi(getenv("B200FFT_PDL")) == 0);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)ps.ntiles);
+        cfg.blockDim = dim3(ps.k->threads);
+        cfg.dynamicSmemBytes = ps.k->smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+        ce = cudaLaunchKernelExC(&cfg, ps.k->func, args);
       }
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (ps.kind == PK_CLUSTER) {
@@ -1450,10 +1477,8 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
       FusedParams fp = ps.fp;
       fp.a.swap_in = inverse && first;
       fp.b.swap_out = inverse && last;
-      const size_t cb = Builder::counters_bytes(fp.nbands);
-      unsigned* counters = (unsigned*)band;
-      void* mid = ps.mid_in_dst ? dst : (void*)((char*)band + cb);
-      ce = cudaMemsetAsync(counters, 0, cb, stream);
+      unsigned* counters = (unsigned*)((char*)band + p->band_slot_bytes + ps.counter_off);
+      void* mid = ps.mid_in_dst ? dst : band;
       float scf = (float)sc;
       double scd = sc;
       void* args[] = {&fp, (void*)&src, (void*)&dst, (void*)&mid, (void*)&ps.tws, (void*)&ps.twsB, (void*)&ps.tw_lo, (void*)&ps.tw_hi,
@@ -1465,9 +1490,8 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
       BandParams bp = ps.bp;
       bp.swap_in = inverse && first;
       bp.swap_out = inverse && last;
-      const size_t cb = Builder::counters_bytes(bp.nbands);
-      unsigned* counters = (unsigned*)band;
-      void* slots = (void*)((char*)band + cb);
+      unsigned* counters = (unsigned*)((char*)band + p->band_slot_bytes + ps.counter_off);
+      void* slots = band;
       alignas(64) CUtensorMap tm;
       cuuint64_t dims[4] = {ps.tm_dims[0], ps.tm_dims[1], ps.tm_dims[2], ps.tm_dims[3]};
       cuuint64_t strides[3] = {ps.tm_strides[0], ps.tm_strides[1], ps.tm_strides[2]};
@@ -1477,7 +1501,6 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
                                                const_cast<void*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (cr != CUDA_SUCCESS) { status = B200FFT_EXEC_FAILED; break; }
-      ce = cudaMemsetAsync(counters, 0, cb, stream);
       float scf = (float)sc;
       double scd = sc;
       void* args[] = {(void*)&tm, (void*)&bp, (void*)&dst, (void*)&slots, (void*)&ps.tws, (void*)&ps.twsB, (void*)&ps.tw_lo, (void*)&ps.tw_hi,

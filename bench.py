@@ -202,7 +202,7 @@ def main_reference(args):
     }
     if "fftw_standin" in base:
         line["fftw_standin"] = base["fftw_standin"]
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -657,11 +657,30 @@ def main_gpu(args):
             line["configs"] = configs
         if slab is not None:
             line["slab"] = slab
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on the first
+    communicator, torchrun children inherit the descriptor): everything but the final line goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -679,6 +698,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         return main_reference(args)
     return main_gpu(args)
