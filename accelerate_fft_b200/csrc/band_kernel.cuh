@@ -259,9 +259,12 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
         __threadfence();
         fence_proxy_async_all();
         for (; seen < cnt; seen++) red_add_relaxed_gpu(counters + sig[lane * 16 + 8 + (seen & 7)], 1u);
-        if (!fin) sig[lane * 16 + 3] = seen;      // the group may re-use ring entries below this
+        // the group may re-use ring entries below this (release: the reads of the entries above are ordered before it)
+        if (!fin) asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32((const void*)&sig[lane * 16 + 3])), "r"(seen) : "memory");
       } else {
-        if (!fin && sig[lane * 16 + 1] != 0) {   // the group has left: one more look at its count, then done
+        int left = 0;
+        if (!fin) asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(left) : "r"(smem_u32((const void*)&sig[lane * 16 + 1])) : "memory");
+        if (!fin && left != 0) {   // the group has left: one more look at its count, then done
           asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(cnt) : "r"(smem_u32((const void*)&sig[lane * 16])) : "memory");
           if (cnt == seen) fin = true;
         }
@@ -305,7 +308,7 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
       __nanosleep(64);
     }
     if (d.x < 0) {
-      if (tid == 0) sig[grp * 16 + 1] = 1;
+      if (tid == 0) asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32((const void*)&sig[grp * 16 + 1])), "r"(1) : "memory");
       break;
     }
     const int band = d.y;
@@ -365,7 +368,15 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
       }
       group_bar(gbar, GT);                      // all of the tile's stores have been issued; the exchange space is free again
       if (tid == 0) {                           // hand the tile to the signaller warp (fence + counter bump off this path)
-        while (na_done - sig[grp * 16 + 3] >= 8) __nanosleep(50);   // ring of 8 (the signaller is normally at most 1-2 behind)
+        // single-producer / single-consumer ring of 8 band numbers with the signaller warp (it is normally at most 1-2 behind):
+        // entries are published by the release store of the count below and recycled through the signaller's release store of
+        // its read position -- ordered by acquire / release on the two counters, not by a barrier (compute-sanitizer's racecheck
+        // only knows barriers and reports these four accesses, profiles/r02_compute_sanitizer.txt)
+        int consumed;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(consumed) : "r"(smem_u32((const void*)&sig[grp * 16 + 3])) : "memory");
+          if (na_done - consumed >= 8) __nanosleep(50);
+        } while (na_done - consumed >= 8);
         sig[grp * 16 + 8 + (na_done & 7)] = band;
         asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32((const void*)&sig[grp * 16])), "r"(na_done + 1) : "memory");
       }

@@ -1433,24 +1433,27 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
         g.peer[0] = (char*)dst + (size_t)(ps.k->N / 2) * (size_t)g.ons * esz;
         g.peer[1] = dst;
       }
+      // Programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream drains (its CTAs
+      // take the SMs the predecessor's last wave leaves idle and sit in griddepcontrol.wait until it has completed and
+      // flushed), so back-to-back transforms lose the launch latency and the scheduling ramp between them.  The lines and
+      // ring kernels touch no global memory before that wait, so stream order is what it always was.
+      static const bool pdl = !(getenv("B200FFT_PDL") && atoi(getenv("B200FFT_PDL")) == 0);
+      cudaLaunchConfig_t cfg{};
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
       if (!rotate && ps.ring && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
         g.ntl = ps.ring_ntl;
-        ce = cudaLaunchKernel(ps.ring->func, dim3((unsigned)ps.ring_grid), dim3(ps.ring->threads), args, ps.ring->smem, stream);
+        cfg.gridDim = dim3((unsigned)ps.ring_grid);
+        cfg.blockDim = dim3(ps.ring->threads);
+        cfg.dynamicSmemBytes = ps.ring->smem;
+        ce = cudaLaunchKernelExC(&cfg, ps.ring->func, args);
       } else {
-        // Programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream drains (its CTAs
-        // take the SMs the predecessor's last wave leaves idle and sit in griddepcontrol.wait until it has completed and
-        // flushed), so back-to-back transforms lose the launch latency and the scheduling ramp between them.  The lines
-        // kernel touches no global memory before that wait, so stream order is what it always was.
-        static const bool pdl = !(getenv("B200FFT_PDL") && atoi(getenv("B200FFT_PDL")) == 0);
-        cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)ps.ntiles);
         cfg.blockDim = dim3(ps.k->threads);
         cfg.dynamicSmemBytes = ps.k->smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
         ce = cudaLaunchKernelExC(&cfg, ps.k->func, args);
       }
       g_launches.fetch_add(1, std::memory_order_relaxed);

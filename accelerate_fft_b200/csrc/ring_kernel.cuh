@@ -98,11 +98,15 @@ fft_ring_rows_kernel(const Geom g, const cpx_t<typename R::Base::real>* __restri
     bulk_g2s(smem_raw + R::STAGE_BYTES * s, in + line0 * K::N, bytes, &full[s]);
   };
 
+  // programmatic dependent launch (plan.cu): the next kernel on the stream may be scheduled while this one drains; this one
+  // sets up its barriers while its predecessor drains and touches global memory only after the predecessor has completed
+  asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0) {
     for (int s = 0; s < R::NS; s++) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0)
     for (int k = 0; k < R::NS && k < nk; k++) issue(k);
 

@@ -520,6 +520,51 @@ SHAPES_3D = [(1, 1, 1), (2, 2, 2), (16, 32, 64), (64, 32, 16), (10, 12, 14), (3,
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_slab_entry_point_single_rank(af, oracle, dtype):
+    """The multi-GPU entry point of the C ABI (b200fftPlanSlab3d / b200fftExecSlab, csrc/slab.cu) with ONE rank: the exchange
+    degenerates to scattering into this GPU's own receive buffer, but the whole pipeline runs -- window plans, the chunked
+    y pass as a grid-stride loop on a few CTAs, side streams, flag barriers, both output layouts, the Inverse scale -- so it
+    is exercised on a one-GPU box too (two ranks over NVLink: tests/test_multigpu.py).  Against the oracle's fft3D."""
+    import ctypes
+    import torch
+    from accelerate_fft_b200._lib import ALLGATHER_FN
+    lib = af.lib()
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    rng = np.random.default_rng(77)
+
+    def allgather(_ctx, send, recv, nbytes):          # one rank: the gathered blob is my own
+        ctypes.memmove(recv, send, nbytes)
+        return 0
+
+    cb = ALLGATHER_FN(allgather)
+    for (d, h, w) in [(16, 32, 64), (64, 128, 96), (256, 64, 512)]:
+        x = rand_complex(rng, (d, h, w), dtype)
+        ref = oracle.fft3D("Forward", x, threads=8)
+        xd = torch.from_numpy(x).cuda()
+        hnd = ctypes.c_void_p()
+        assert lib.b200fftPlanSlab3d(ctypes.byref(hnd), d, h, w, typ, 0, 1, 1, cb, None) == 0
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for (cp, ck, yc) in [(None, None, None), (1, 1, 0), (2, 2, 5), (4, 3, 40)]:
+            if cp is not None:
+                assert lib.b200fftSlabTune(hnd, 0, cp, ck, yc) == 0 and lib.b200fftSlabTune(hnd, 1, cp, ck, yc) == 0
+            nat = torch.empty_like(xd)
+            tr = torch.empty((h, d, w), dtype=xd.dtype, device="cuda")
+            assert lib.b200fftExecSlab(hnd, xd.data_ptr(), nat.data_ptr(), af.FORWARD, 1.0, 0, st) == 0
+            assert lib.b200fftExecSlab(hnd, xd.data_ptr(), tr.data_ptr(), af.FORWARD, 1.0, 1, st) == 0
+            assert rel_l2(nat.cpu().numpy(), ref) <= bar(dtype, x.size), ((d, h, w), cp, ck, yc)
+            assert rel_l2(tr.cpu().numpy().transpose(1, 0, 2), ref) <= bar(dtype, x.size), ((d, h, w), cp, ck, yc)   # [H][D][W]
+            back = torch.empty_like(xd)
+            assert lib.b200fftExecSlab(hnd, nat.data_ptr(), back.data_ptr(), af.INVERSE, 1.0 / x.size, 0, st) == 0
+            assert rel_l2(back.cpu().numpy(), x) <= 2 * bar(dtype, x.size)
+        buf = ctypes.c_void_p()
+        assert lib.b200fftSlabNaturalBuffer(hnd, ctypes.byref(buf)) == 0 and buf.value
+        assert lib.b200fftExecSlab(hnd, xd.data_ptr(), xd.data_ptr(), af.FORWARD, 1.0, 0, st) != 0     # in == out is refused
+        assert lib.b200fftDestroySlab(hnd) == 0
+    hnd = ctypes.c_void_p()
+    assert lib.b200fftPlanSlab3d(ctypes.byref(hnd), 48, 32, 16, typ, 0, 1, 1, cb, None) == 16            # D not a power of two: NOT_SUPPORTED
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode", MODES)
 def test_fft3d_vs_oracle(af, oracle, dtype, mode):
     rng = np.random.default_rng(15)
