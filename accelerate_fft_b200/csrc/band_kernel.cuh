@@ -56,7 +56,8 @@ struct BandParams {
   long long otw_col0;            // OUTER: column index of band (bo = 0, bi = 0), columns advance by Wb per bi
   int swap_in, swap_out;         // conjugate on load (phase A) / on store (phase B)
   int wb;                        // STRIDED: columns per band
-  int debug;                     // developer timing experiments: 1 ignore dependencies, 2 phase A only, 3 phase B only (results invalid)
+  int debug;                     // developer timing experiments (results invalid): low 3 bits 1 ignore dependencies, 2 phase A only,
+                                 // 3 phase B only; +8 no butterflies, +16 no global stores, +32 no loads (stages 'land' at once)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -171,8 +172,8 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
     const unsigned totA = (unsigned)p.nbands * nA, totB = (unsigned)p.nbands * nB;
     unsigned nTA = (totA > blockIdx.x) ? (totA - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     unsigned nTB = (totB > blockIdx.x) ? (totB - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-    if (p.debug == 2) nTB = 0;
-    if (p.debug == 3) nTA = 0;
+    if ((p.debug & 7) == 2) nTB = 0;
+    if ((p.debug & 7) == 3) nTA = 0;
     const bool isA = lane >= 16;
     unsigned ia = 0, ib = 0, iss = 0;
     while (ia < nTA || ib < nTB) {
@@ -186,7 +187,7 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
       // used its scratch slot before has been pulled completely
       bool ready = false;
       if (valid) {
-        if (p.debug) ready = true;
+        if (p.debug & 7) ready = true;
         else if (!isA) ready = ld_acquire_gpu(counters + band) >= nA;
         else ready = band < p.nslots || ld_acquire_gpu(counters + p.nbands + (band - p.nslots)) >= nB;
       }
@@ -205,7 +206,9 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
         if (i >= (unsigned)NST) mbar_wait(&empty[st], ((i / NST) - 1) & 1);
         const int bo = band / p.nbi, bi = band % p.nbi;
         desc[st] = make_int4(isA ? 0 : 1, band, (int)tile, (int)i);
-        if (isA) {
+        if (p.debug & 32) {
+          mbar_arrive(&full[st]);     // experiment: no copy at all
+        } else if (isA) {
           mbar_expect_tx(&full[st], (uint32_t)P::A_BYTES);
           const int u = (int)(tile / (unsigned)p.a_ncg), cg = (int)(tile % (unsigned)p.a_ncg);
           if constexpr (P::MODE == MODE_STRIDED)   // dims {2 I, N2, N1, O}: box {2 TLA, 1, N1, 1}
@@ -324,25 +327,28 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
       static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = land[(t + e * K::TPT) * K::TL + l]; });
       mbar_arrive(&empty[st]);                  // pulled: the loader may refill the stage
       if (p.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
-      run_stage<K, 0, C, false>(v, t, stwA);
-      scatter<K, 0, true>(v, xch, l, t);
-      static_for<1, K::S - 1>([&](auto sc) {
-        constexpr int s = sc;
-        group_bar(gbar, GT);
-        gather<K, true>(v, xch, l, t);
-        run_stage<K, s, C, false>(v, t, stwA);
-        group_bar(gbar, GT);
-        scatter<K, s, true>(v, xch, l, t);
-      });
+      const bool nomath = (p.debug & 8) != 0, nostore = (p.debug & 16) != 0;   // developer timing experiments (results invalid)
+      if (!nomath) {
+        run_stage<K, 0, C, false>(v, t, stwA);
+        scatter<K, 0, true>(v, xch, l, t);
+        static_for<1, K::S - 1>([&](auto sc) {
+          constexpr int s = sc;
+          group_bar(gbar, GT);
+          gather<K, true>(v, xch, l, t);
+          run_stage<K, s, C, false>(v, t, stwA);
+          group_bar(gbar, GT);
+          scatter<K, s, true>(v, xch, l, t);
+        });
+      }
       if (tid == 0) sig[grp * 16 + 2] = atomicAdd(claim, 1);
       group_bar(gbar, GT);
-      gather<K, true>(v, xch, l, t);
+      if (!nomath) gather<K, true>(v, xch, l, t);
       seq = (unsigned)sig[grp * 16 + 2];
-      run_stage<K, K::S - 1, C, false>(v, t, stwA);
+      if (!nomath) run_stage<K, K::S - 1, C, false>(v, t, stwA);
       const int u = (int)(tile / (unsigned)p.a_ncg), cg = (int)(tile % (unsigned)p.a_ncg);
       // inner four-step twiddle w_{N1 N2}^(k1 * n2), k1 = t + e*TPT: an anchor per 8 points + a running product
       const unsigned m = (P::MODE == MODE_STRIDED) ? (unsigned)u : (unsigned)(cg * TLA + l);
-      {
+      if (!nomath) {
         constexpr int CH = (K::E < 8) ? K::E : 8;
         const C stepw = root((unsigned)K::TPT * m);
         static_for<0, K::E / CH>([&](auto qc) {
@@ -356,7 +362,9 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
         });
       }
       C* sl = slots + (long long)(band % p.nslots) * p.slot_elems;
-      if constexpr (P::MODE == MODE_STRIDED) {
+      if (nostore) {
+        if (v[0].x == (T)123.456f && v[1].y == (T)654.321f) sl[tid] = v[2];   // (keeps the values alive)
+      } else if constexpr (P::MODE == MODE_STRIDED) {
         // slot [cB][k1][n2][TLB], column c = cg*TLA + l of the band, n2 = u
         const int c = cg * TLA + l;
         C* op = sl + ((long long)(c / TLB) * N1 + t) * (N2 * TLB) + u * TLB + (c % TLB);
@@ -392,23 +400,26 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
       else static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = land[(t + e * K::TPT) * K::TL + l]; });
       mbar_arrive(&empty[st]);
       if (tid == 0) red_add_relaxed_gpu(counters + p.nbands + band, 1u);   // the slot's data for this tile has been copied out
-      run_stage<K, 0, C, false>(v, t, stwB);
-      scatter<K, 0, !ROWS>(v, xch, l, t);
-      static_for<1, K::S - 1>([&](auto sc) {
-        constexpr int s = sc;
-        group_bar(gbar, GT);
-        gather<K, !ROWS>(v, xch, l, t);
-        run_stage<K, s, C, false>(v, t, stwB);
-        group_bar(gbar, GT);
-        scatter<K, s, !ROWS>(v, xch, l, t);
-      });
+      const bool nomath = (p.debug & 8) != 0, nostore = (p.debug & 16) != 0;   // developer timing experiments (results invalid)
+      if (!nomath) {
+        run_stage<K, 0, C, false>(v, t, stwB);
+        scatter<K, 0, !ROWS>(v, xch, l, t);
+        static_for<1, K::S - 1>([&](auto sc) {
+          constexpr int s = sc;
+          group_bar(gbar, GT);
+          gather<K, !ROWS>(v, xch, l, t);
+          run_stage<K, s, C, false>(v, t, stwB);
+          group_bar(gbar, GT);
+          scatter<K, s, !ROWS>(v, xch, l, t);
+        });
+      }
       if (tid == 0) sig[grp * 16 + 2] = atomicAdd(claim, 1);
       group_bar(gbar, GT);
       if constexpr (ROWS) { l = tid % K::TL; t = tid / K::TL; }   // store mapping: line-fastest
-      gather<K, !ROWS>(v, xch, l, t);
+      if (!nomath) gather<K, !ROWS>(v, xch, l, t);
       seq = (unsigned)sig[grp * 16 + 2];
       group_bar(gbar, GT);                      // every thread has gathered: the exchange space is free for the next tile
-      run_stage<K, K::S - 1, C, false>(v, t, stwB);
+      if (!nomath) run_stage<K, K::S - 1, C, false>(v, t, stwB);
       // output index k = k1 + N1*k2, k2 = t + e*TPT
       int k1, cb;          // STRIDED: tile = cB*N1 + k1; ROWS: tile = k1
       if constexpr (P::MODE == MODE_STRIDED) { cb = (int)(tile / (unsigned)N1); k1 = (int)(tile % (unsigned)N1); } else { cb = 0; k1 = (int)tile; }
@@ -436,10 +447,14 @@ fft_band_kernel(const __grid_constant__ CUtensorMap tmA, const BandParams p, cpx
       C* op = out + (long long)bo * p.out_bo + (long long)bi * p.out_bi + (long long)(k1 + N1 * t) * p.out_ks + cb * TLB + l;
       const unsigned step_b = (unsigned)((long long)N1 * K::TPT * p.out_ks * (long long)sizeof(C));
       char* pb = reinterpret_cast<char*>(op);
-      static_for<0, K::E>([&](auto ec) {
-        constexpr int e = ec;
-        st_stream(reinterpret_cast<C*>(pb + (unsigned long long)(unsigned)e * step_b), v[e]);
-      });
+      if (nostore) {
+        if (v[0].x == (T)123.456f && v[1].y == (T)654.321f) *op = v[2];   // (keeps the values alive)
+      } else {
+        static_for<0, K::E>([&](auto ec) {
+          constexpr int e = ec;
+          st_stream(reinterpret_cast<C*>(pb + (unsigned long long)(unsigned)e * step_b), v[e]);
+        });
+      }
     }
   }
 }

@@ -1,9 +1,5 @@
 #!/bin/bash
-for v in 0 1; do
-  for c in 3 4; do
-    echo -n "variant=$v  "
-    B200FFT_BAND_VARIANT=$v python tools/quick_bench.py $c | cut -c1-130
-  done
+# band kernel stream isolation on cfg3 (rows pass ~200 us in every line): debug = mode + 8 nomath + 16 nostore + 32 noload
+for d in 0 2 3 10 11 26 27 42 43 58 59; do
+  echo -n "debug=$d  "; B200FFT_BAND_DEBUG=$d python tools/quick_bench.py 3 | cut -c1-60
 done
-echo "== variant=0 prof"
-B200FFT_BAND_PROF=1 python tools/quick_bench.py 3 2>&1 | tail -2 | cut -c1-400
