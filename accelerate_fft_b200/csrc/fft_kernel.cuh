@@ -356,6 +356,11 @@ __device__ __forceinline__ void fft_small_rows_tile(const Geom& g, unsigned tile
   });
 }
 
+// `in` and `out` carry __restrict__ although the planner runs some passes in place (src == dst: column passes of 2D / 3D
+// plans, four-step first passes).  That is sound here for a reason the type system cannot see: a tile reads and writes exactly
+// the same set of elements, all of its loads complete (they feed the first register stage, and at least one barrier follows)
+// before its first store is issued, and no tile touches another tile's elements -- so no load can observe a store of the same
+// launch, through the read-only path or otherwise.  tests/test_parity_gpu.py runs every in-place pass against the oracle.
 template <class K, bool LLF, bool SLF, bool TW4, bool PRE2 = false>
 __global__ void __launch_bounds__(K::THREADS, K::MINB)
 fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, cpx_t<typename K::real>* __restrict__ out,
@@ -373,7 +378,13 @@ fft_lines_kernel(const Geom g, const cpx_t<typename K::real>* __restrict__ in, c
       return;
     }
   }
-  fft_lines_tile<K, LLF, SLF, TW4, false, 0, PRE2>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
+#ifndef B200FFT_ROW_HINT
+#define B200FFT_ROW_HINT 0
+#endif
+  // cache hints for long contiguous rows (bit 0 evict-first loads, bit 1 evict-first stores), compile-time experiment: measured on
+  // B200, c64 8192-point rows: no hint 195.3 us, loads 216.6, stores 194.3, both 206.7 (cfg3 471 / 494 / 471 / 503 us) -- left off
+  constexpr int HINT = (!LLF && !SLF && !TW4 && !PRE2 && K::N >= 2048) ? B200FFT_ROW_HINT : 0;
+  fft_lines_tile<K, LLF, SLF, TW4, false, HINT, PRE2>(g, blockIdx.x, in, out, tws, tw_lo, tw_hi, scale, reinterpret_cast<C*>(smem_raw));
 }
 
 // The same tile function under a grid-stride loop: the launch decides how many CTAs (hence SMs) the pass occupies.  Used by
