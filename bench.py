@@ -101,6 +101,8 @@ class ClockSampler:
 
 
 def dominant_kernel(plan_desc):
+    if any("band A[" in d for d in plan_desc):
+        return "fft_band_kernel (+ fft_lines_kernel rows)"
     if any("| ring:" in d for d in plan_desc):
         return "fft_ring_rows_kernel"
     if any("| pipe" in d for d in plan_desc):
