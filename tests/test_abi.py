@@ -88,3 +88,38 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def _build_c_smoke(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(ROOT, "accelerate_fft_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L" + libdir, "-lb200fft", "-lm",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr          # include/b200fft.h is valid, warning-free C99
+    return exe
+
+
+def test_header_is_c_and_the_library_links_from_plain_c(tmp_path):
+    """include/b200fft.h compiles as pedantic C99 and a plain-C host (no CUDA headers, no C++, no Python) links the library and
+    calls it; without a GPU the call must fail loudly with B200FFT_NO_DEVICE (exit code 3), never fall back."""
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "NO_DEVICE" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_plain_c_host_computes_a_correct_transform(tmp_path):
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "max abs error" in r.stdout, (r.returncode, r.stdout, r.stderr)
