@@ -30,6 +30,10 @@ void register_ring(void (*add)(const KernelEntry&)) {
   // requested from HBM at kernel start instead of wave by wave
   REG_RING(4, 12, float, 1024, 16, 2, 1, 16, 16, 4);     // v0: 4 groups x 128 thr, 12 x 17 KB stages
   REG_RING(8, 24, float, 1024, 16, 1, 1, 16, 16, 4);     // v1: 8 groups x 64 thr, 24 x 8.5 KB stages
+  // 128 KB lines (c64 N=16384, c128 N=8192): one CTA per SM and no room for a second buffer -- a "ring" of ONE stage still lets the
+  // TMA engine fetch the next line while the last register stage and the stores of the current one run
+  REG_RING(1, 1, float, 16384, 32, 1, 1, 32, 32, 16);
+  REG_RING(1, 1, double, 8192, 16, 1, 1, 16, 16, 16, 2);
   // measured on B200 (profiles/r01_ring_vs_plain.txt): the ring wins only where FP64 + 68 KB tiles leave the plain
   // kernel latency-bound (c128 N=4096: 81.7 % -> 88.4 % of measured HBM peak).  It loses for c128 N=2048
   // (93.0 % vs 96.3 %), c64 N=8192 (73.5 % vs 80.4 %) and c64 N=4096 (81.3 % vs 91.6 %), where the extra

@@ -348,7 +348,7 @@ struct Builder {
       // short c64 rows: the ring only pays for small batches (the plain kernel streams big ones at ~100 %)
       // (opt-in via B200FFT_RING_C64_MAX_LINES; measured slower than the plain kernel at every batch size,
       //  cfg1: 19.7-20.7 us against 16.7 us -- profiles/r01_pair2d_and_narrow_columns.txt)
-      if (r && !p->is_double && g.nl > env_int("B200FFT_RING_C64_MAX_LINES", 0)) r = nullptr;
+      if (r && !p->is_double && N < 16384 && g.nl > env_int("B200FFT_RING_C64_MAX_LINES", 0)) r = nullptr;
       // worth it only when every SM gets a few tiles to pipeline
       if (r && (g.nl + r->TL - 1) / r->TL >= 2LL * 148) {
         ps.ring = r;
@@ -1594,6 +1594,9 @@ int b200fftExecScatterOn(b200fftHandle p, const void* in, void* const* outs, int
 // Device buffers that other processes of the box can map (CUDA IPC): the peer buffers of b200fftExecScatter.
 int b200fftPeerAlloc(void** ptr, size_t bytes) {
   if (!ptr || !bytes) return B200FFT_INVALID_VALUE;
+  // whole multiples of 2 MiB: smaller cudaMalloc requests are carved out of shared 2 MiB blocks and an IPC handle names the
+  // block, not the piece
+  bytes = (bytes + ((size_t)2 << 20) - 1) / ((size_t)2 << 20) * ((size_t)2 << 20);
   if (cudaMalloc(ptr, bytes) != cudaSuccess) { cudaGetLastError(); return B200FFT_ALLOC_FAILED; }
   return B200FFT_SUCCESS;
 }

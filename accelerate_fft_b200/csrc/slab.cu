@@ -143,8 +143,11 @@ int b200fftPlanSlab3d(b200fftSlabHandle* plan, int64_t d, int64_t h, int64_t w, 
   s->d = d; s->h = h; s->w = w; s->dl = d / nranks; s->hl = h / nranks;
   auto fail = [&](int e) { b200fftDestroySlab(s); return e; };
   const size_t slab_bytes = (size_t)s->dl * h * w * s->esz;     // == D * hl * W
-  if (cudaMalloc(&s->tmp, slab_bytes) != cudaSuccess || cudaMalloc(&s->recv, slab_bytes) != cudaSuccess ||
-      (s->natural && cudaMalloc(&s->back, slab_bytes) != cudaSuccess) || cudaMalloc(&s->flags, 256) != cudaSuccess) {
+  // Buffers whose IPC handles go to the peers are whole multiples of 2 MiB: the driver carves smaller cudaMalloc requests out of
+  // shared 2 MiB blocks, and an IPC handle names the block, not the piece -- a peer would map the block's base.
+  auto ipc_size = [](size_t b) { const size_t g = (size_t)2 << 20; return (b + g - 1) / g * g; };
+  if (cudaMalloc(&s->tmp, slab_bytes) != cudaSuccess || cudaMalloc(&s->recv, ipc_size(slab_bytes)) != cudaSuccess ||
+      (s->natural && cudaMalloc(&s->back, ipc_size(slab_bytes)) != cudaSuccess) || cudaMalloc(&s->flags, ipc_size(256)) != cudaSuccess) {
     cudaGetLastError();
     return fail(B200FFT_ALLOC_FAILED);
   }
