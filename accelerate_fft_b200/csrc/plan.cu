@@ -63,6 +63,7 @@ static void ensure_registry() {
     register_pair(add_entry);
     register_cluster(add_entry);
     register_pipe(add_entry);
+    register_ringcol(add_entry);
     register_fused(add_fused);
     register_band(add_band);
   });
@@ -202,6 +203,10 @@ struct Pass {
   // PK_BAND: two phases fused through L2 (band_kernel.cuh); tws / twsB = stage twiddles, tw_lo / tw_hi = inner four-step table
   const BandEntry* bz = nullptr;
   BandParams bp{};
+  // persistent single-buffer TMA-fed column kernel (ringcol_kernel.cuh) for tiles that fill an SM; rctws = its stage twiddles
+  const KernelEntry* ringcol = nullptr;
+  void* rctws = nullptr;
+  int ringcol_ntl = 0, ringcol_grid = 0;
   size_t slot_bytes = 0, counter_bytes = 0, counter_off = 0;   // fused / band passes: their share of the plan's band scratch
   void* otw_lo = nullptr;          // outer four-step table (OUTER kernels)
   void* otw_hi = nullptr;
@@ -358,6 +363,7 @@ struct Builder {
       }
     }
     if (flavor == FL_COL) attach_pipe(ps, N, tw4);
+    if (flavor == FL_COL && !tw4 && !ps.pipe) attach_ringcol(ps, N);
     if (flavor == FL_ROW && !tw4) attach_pipe_rows(ps, N);
     push(ps);
     return true;
@@ -376,6 +382,30 @@ struct Builder {
       return upload(p, h);
     };
     return p->is_double ? build(double{}) : build(float{});
+  }
+
+  // Column tiles that fill an SM's shared memory (one lock-step CTA per SM, load / butterflies / store in turn): the persistent
+  // single-buffer TMA-fed kernel fetches the next tile while the last stage and the stores of the current one run.
+  void attach_ringcol(Pass& ps, long long N) {
+    if (getenv("B200FFT_RINGCOL") && atoi(getenv("B200FFT_RINGCOL")) == 0) return;
+    const KernelEntry* q = find_kernel(p->is_double, (int)N, FL_RINGCOL, 0, 0);
+    if (!q || ps.k->smem < 100 * 1024) return;
+    const Geom& g = ps.g;
+    const long long esz = p->is_double ? 16 : 8;
+    if (g.nb != 1 || g.ils != 1 || g.ols != 1 || g.nl % q->TL) return;
+    if ((g.ins * esz) % 16 || (g.ios * esz) % 16 || 2LL * g.nl >= (1LL << 32) || g.ins * esz >= (1LL << 40) || g.ios * esz >= (1LL << 40)) return;
+    {
+      const long long tpt = q->N / q->E;
+      if (tpt * g.ons * esz >= (1LL << 32)) return;
+    }
+    const long long ntl = g.nl / q->TL, ntiles = (long long)g.no * ntl;
+    if (ntiles < 148 || ntiles >= (1LL << 31)) return;
+    ps.ringcol = q;
+    ps.ringcol_ntl = (int)ntl;
+    ps.rctws = make_stage_twiddles(p, q);
+    char buf[200];
+    snprintf(buf, sizeof buf, " | ring cols: persistent, TMA-fed, one buffer, TL=%d threads=%d smem=%zu tiles=%lld", q->TL, q->threads, q->smem, ntiles);
+    ps.desc += buf;
   }
 
   // Attach the persistent pipelined kernel to a column pass over [O][N][I] whose Geom is ps.g (ils == ols == 1).
@@ -1183,6 +1213,17 @@ static int set_func_attrs(b200fft_plan_s* p) {
       const long long grid = (long long)nsm * occ;
       ps.band_grid = (int)(grid < ps.ntiles ? grid : ps.ntiles);
     }
+    if (ps.kind == PK_LINES && ps.ringcol) {
+      int dev = 0, nsm = 0, occ = 0;
+      bool ok = cudaFuncSetAttribute(ps.ringcol->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.ringcol->smem) == cudaSuccess &&
+                cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.ringcol->func, ps.ringcol->threads, ps.ringcol->smem) == cudaSuccess && occ > 0;
+      if (!ok) { cudaGetLastError(); ps.ringcol = nullptr; }   // the lock-step kernel still serves the pass
+      else {
+        const long long ntiles = (long long)ps.g.no * ps.ringcol_ntl, grid = (long long)nsm * occ;
+        ps.ringcol_grid = (int)(grid < ntiles ? grid : ntiles);
+      }
+    }
     if (ps.kind == PK_LINES && ps.ring) {
       int dev = 0, nsm = 0, occ = 0;
       bool ok = cudaFuncSetAttribute(ps.ring->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.ring->smem) == cudaSuccess &&
@@ -1338,6 +1379,42 @@ static tensor_map_encode_t tensor_map_encoder() {
   return fn;
 }
 
+// Launch the persistent single-buffer TMA-fed column kernel for a lines pass (ringcol_kernel.cuh); false = not launched (the
+// caller falls back to the lock-step kernel).  g carries swap / peer fields already; max_ctas > 0 limits the grid.
+static bool launch_ringcol(const b200fft_plan_s* p, const Pass& ps, Geom g, const void* src, void* dst, double sc, int max_ctas,
+                           cudaStream_t stream) {
+  const KernelEntry* q = ps.ringcol;
+  if (!q || !tensor_map_encoder() || ((uintptr_t)src & 15)) return false;
+  const unsigned long long esz = p->is_double ? 16 : 8;
+  alignas(64) CUtensorMap tm;
+  // the input as a tensor {2 I (reals of a row piece), N rows, O}; a tile = boxes of {2 TL, rows per box, 1}
+  cuuint64_t dims[3] = {2ull * (unsigned long long)g.nl, (unsigned long long)q->N, (unsigned long long)g.no};
+  cuuint64_t strides[2] = {(unsigned long long)g.ins * esz, (unsigned long long)(g.no > 1 ? g.ios : (long long)q->N * g.ins) * esz};
+  cuuint32_t box[3] = {2u * (unsigned)q->TL, (unsigned)q->N1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (tensor_map_encoder()(&tm, p->is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(src), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  g.ntl = ps.ringcol_ntl;
+  float scf = (float)sc;
+  double scd = sc;
+  void* args[] = {(void*)&tm, &g, (void*)&dst, (void*)&ps.rctws, p->is_double ? (void*)&scd : (void*)&scf};
+  static const bool pdl = !(getenv("B200FFT_PDL") && atoi(getenv("B200FFT_PDL")) == 0);
+  cudaLaunchConfig_t cfg{};
+  const int grid = (max_ctas > 0 && max_ctas < ps.ringcol_grid) ? max_ctas : ps.ringcol_grid;
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(q->threads);
+  cfg.dynamicSmemBytes = q->smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  if (cudaLaunchKernelExC(&cfg, q->func, args) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
 int b200fftExecScaled(b200fftHandle p, const void* in, void* out, int direction, double scale, b200fftStream stream_) {
   return exec_common(p, in, out, direction, scale, false, stream_);
 }
@@ -1414,6 +1491,15 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
         g_launches.fetch_add(1, std::memory_order_relaxed);
       } else {
         cudaGetLastError();   // e.g. cluster launches refused under a partitioned device: the lock-step kernel serves the pass
+      }
+    }
+    if (!pipe_done && !rotate && ps.kind == PK_LINES && ps.ringcol) {
+      Geom g = ps.g;
+      g.swap_in = inverse && first;
+      g.swap_out = inverse && last;
+      if (launch_ringcol(p, ps, g, src, dst, sc, 0, stream)) {
+        pipe_done = true;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
       }
     }
     if (pipe_done) {
@@ -1569,7 +1655,9 @@ int b200fftExecScatterOn(b200fftHandle p, const void* in, void* const* outs, int
   cudaError_t ce;
   // NVLink wants long runs: the lock-step kernel stores 128 B per row (TL = 16), the pipelined one 64 B -- measured on
   // 2 x B200, 1024^3: 6.24 ms against 8.30 ms per transform -- so the pipelined kernel only serves a single target
-  if (max_ctas > 0 && ps.k->loop_func) {
+  if (launch_ringcol(p, ps, g, in, dst, scale, max_ctas, stream)) {
+    ce = cudaSuccess;
+  } else if (max_ctas > 0 && ps.k->loop_func) {
     if (ps.k->smem > 48 * 1024) cudaFuncSetAttribute(ps.k->loop_func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem);
     unsigned nt = (unsigned)ps.ntiles;
     void* args[] = {&g, (void*)&in, (void*)&dst, (void*)&ps.tws, (void*)&ps.tw_lo, (void*)&ps.tw_hi,

@@ -8,7 +8,8 @@ namespace b200fft {
 // FL_RING: persistent TMA-fed rows (ring_kernel.cuh); FL_ROWPAIR: rows with the radix-2 pre-butterfly (Geom::pre2_off)
 // FL_PIPE: persistent software-pipelined column kernel, CS = 1 or a cluster (pipe_kernel.cuh)
 // FL_CLUSTER: strided lines of length N = N1*CS transformed by a cluster of CS CTAs (cluster_kernel.cuh)
-enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4, FL_CLUSTER = 5, FL_PIPE = 6, FL_PIPEROW = 7, FL_CLUSTERROW = 8 };
+// FL_RINGCOL: persistent single-buffer TMA-fed column kernel for tiles that fill an SM (ringcol_kernel.cuh)
+enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4, FL_CLUSTER = 5, FL_PIPE = 6, FL_PIPEROW = 7, FL_CLUSTERROW = 8, FL_RINGCOL = 9 };
 
 struct KernelEntry {
   int is_double;
@@ -65,5 +66,6 @@ void register_ring(void (*add)(const KernelEntry&));
 void register_pair(void (*add)(const KernelEntry&));
 void register_cluster(void (*add)(const KernelEntry&));
 void register_pipe(void (*add)(const KernelEntry&));
+void register_ringcol(void (*add)(const KernelEntry&));
 
 }  // namespace b200fft
