@@ -363,6 +363,8 @@ struct Builder {
       }
     }
     if (flavor == FL_COL) attach_pipe(ps, N, tw4);
+    // (not beside the pipelined kernel: for the slab transform's NVLink-bound scatter passes it measured no better than the
+    //  lock-step loop kernel -- 8 GPUs 1.92-2.00 ms against 1.93, profiles/r02_slab_cabi.txt)
     if (flavor == FL_COL && !tw4 && !ps.pipe) attach_ringcol(ps, N);
     if (flavor == FL_ROW && !tw4) attach_pipe_rows(ps, N);
     push(ps);
