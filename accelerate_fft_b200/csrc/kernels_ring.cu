@@ -25,7 +25,11 @@ KernelEntry make_ring_entry() {
 #define REG_RING(G, NS, ...) add(make_ring_entry<RingCfg<Cfg<__VA_ARGS__>, G, NS>>())
 
 void register_ring(void (*add)(const KernelEntry&)) {
-  REG_RING(2, 3, double, 4096, 16, 1, 1, 16, 16, 16);    // cfg2: 2 groups x 256 thr, 3 x 68 KB stages
+  // cfg2 (c128 N=4096, 64 KB lines).  v0: two single-stage 256-thread CTAs per SM -- the next line lands while the last register
+  // stage and the stores of the current one run: 1424 us per direction; v1 (B200FFT_VARIANTS=g4096d=1): one CTA of two groups
+  // alternating over three stages: 1442-1450 us (round 1's default); plain kernel: 1.58 ms
+  REG_RING(1, 1, double, 4096, 16, 1, 2, 16, 16, 16);
+  REG_RING(2, 3, double, 4096, 16, 1, 1, 16, 16, 16);
   // small batches of short rows (cfg1: 4096 rows of c64 N=1024 = 14 tiles per SM): the whole share of an SM is
   // requested from HBM at kernel start instead of wave by wave
   REG_RING(4, 12, float, 1024, 16, 2, 1, 16, 16, 4);     // v0: 4 groups x 128 thr, 12 x 17 KB stages
@@ -33,6 +37,7 @@ void register_ring(void (*add)(const KernelEntry&)) {
   // 128 KB lines (c64 N=16384, c128 N=8192): one CTA per SM and no room for a second buffer -- a "ring" of ONE stage still lets the
   // TMA engine fetch the next line while the last register stage and the stores of the current one run
   REG_RING(1, 1, float, 16384, 32, 1, 1, 32, 32, 16);
+  REG_RING(1, 1, float, 8192, 32, 1, 2, 32, 16, 16);      // 64 KB lines, two single-stage CTAs per SM (cfg3's rows)
   REG_RING(1, 1, double, 8192, 16, 1, 1, 16, 16, 16, 2);
   // measured on B200 (profiles/r01_ring_vs_plain.txt): the ring wins only where FP64 + 68 KB tiles leave the plain
   // kernel latency-bound (c128 N=4096: 81.7 % -> 88.4 % of measured HBM peak).  It loses for c128 N=2048

@@ -353,7 +353,7 @@ struct Builder {
       // short c64 rows: the ring only pays for small batches (the plain kernel streams big ones at ~100 %)
       // (opt-in via B200FFT_RING_C64_MAX_LINES; measured slower than the plain kernel at every batch size,
       //  cfg1: 19.7-20.7 us against 16.7 us -- profiles/r01_pair2d_and_narrow_columns.txt)
-      if (r && !p->is_double && N < 16384 && g.nl > env_int("B200FFT_RING_C64_MAX_LINES", 0)) r = nullptr;
+      if (r && !p->is_double && N < env_int("B200FFT_RING_C64_MIN_N", 8192) && g.nl > env_int("B200FFT_RING_C64_MAX_LINES", 0)) r = nullptr;
       // worth it only when every SM gets a few tiles to pipeline
       if (r && (g.nl + r->TL - 1) / r->TL >= 2LL * 148) {
         ps.ring = r;

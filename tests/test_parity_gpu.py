@@ -72,7 +72,7 @@ def test_fft_pow2_vs_oracle(af, oracle, dtype, mode):
             assert rel_l2(y[:1], ex.astype(np.complex128)) <= bar(dtype, n) / 2, (n, mode)
 
 
-@pytest.mark.parametrize("n,dtype", [(4096, np.complex128), (16384, np.complex64), (8192, np.complex128)])
+@pytest.mark.parametrize("n,dtype", [(4096, np.complex128), (16384, np.complex64), (8192, np.complex128), (8192, np.complex64)])
 @pytest.mark.parametrize("mode", ["Forward", "Inverse"])
 def test_persistent_tma_row_kernel_vs_oracle(af, oracle, n, dtype, mode):
     """Batches large enough (>= 2 tiles per SM) take the persistent TMA-fed ring kernel (ring_kernel.cuh);
@@ -99,6 +99,12 @@ def test_persistent_tma_row_kernel_vs_oracle(af, oracle, n, dtype, mode):
         os.environ["B200FFT_NO_RING"] = "0"
         af.lib().accfft_plan_cache_clear()
     assert np.array_equal(y, y2)
+    if n == 4096:     # the registered alternative (one CTA of two groups alternating over three stages, round 1's default)
+        with _env(af, B200FFT_VARIANTS="g4096d=1"):
+            p = af.Plan("many", [n], af.Z2Z, batch)
+            assert "ring: G=2 NS=3" in p.describe(), p.describe()
+            p.destroy()
+            assert np.array_equal(y, gpu(af, "fft", mode, x))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
