@@ -571,6 +571,43 @@ def test_slab_entry_point_single_rank(af, oracle, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", ["Forward", "Inverse"])
+def test_single_buffer_tma_column_kernel(af, oracle, dtype, mode):
+    """1024-point columns whose 128 KB tile fills an SM: the persistent single-buffer TMA-fed column kernel (ringcol_kernel.cuh,
+    cfg5's z axis) -- taken when the pipelined column kernel is not (here: switched off), from 148 tiles on; against the oracle's
+    fft2D, bit-identical to the lock-step kernel, and the fallback for a buffer TMA cannot address."""
+    import torch
+    tl = 16 if dtype == np.complex64 else 8
+    typ = af.C2C if dtype == np.complex64 else af.Z2Z
+    w = 150 * tl
+    rng = np.random.default_rng(91)
+    x = rand_complex(rng, (1024, w), dtype)
+    with _env(af, B200FFT_PIPE="0"):
+        p = af.Plan("2d", [1024, w], typ, 1)
+        assert "ring cols" in p.describe(), p.describe()
+        p.destroy()
+        y = gpu(af, "fft2D", mode, x)
+        with _env(af, B200FFT_PIPE="0", B200FFT_RINGCOL="0"):
+            y0 = gpu(af, "fft2D", mode, x)
+        # the column pass alone: an input TMA cannot address (element-aligned only) takes the lock-step kernel, same result
+        pa = af.Plan("axis", (1, 1024, w), typ)
+        assert "ring cols" in pa.describe(), pa.describe()
+        xd = torch.from_numpy(x).cuda()
+        buf = torch.empty(x.size + 1, dtype=xd.dtype, device="cuda")
+        xin = buf[1:].view(1024, w)
+        xin.copy_(xd)
+        oa, ob = torch.empty_like(xd), torch.empty_like(xd)
+        pa.exec(xd, oa, af.FORWARD)
+        if xin.data_ptr() % 16:
+            pa.exec(xin, ob, af.FORWARD)
+            assert torch.equal(oa, ob)
+        pa.destroy()
+        assert rel_l2(oa.cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=0)) <= bar(dtype, 1024)
+    assert rel_l2(y, oracle.fft2D(mode, x, threads=8)) <= bar(dtype, x.size)
+    assert np.array_equal(y, y0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode", MODES)
 def test_fft3d_vs_oracle(af, oracle, dtype, mode):
     rng = np.random.default_rng(15)

@@ -29,6 +29,30 @@ for dt in (np.complex64, np.complex128):
     for x, y in zip([x for x in xs for _ in range(2)], ys):
         assert rel(y.cpu().numpy(), np.fft.fft(x.cpu().numpy().astype(np.complex128), axis=-1)) < 1e-4
     print("pdl back-to-back ok", np.dtype(dt).name, flush=True)
+for dt, n in ((np.complex64, 16384), (np.complex64, 8192), (np.complex128, 8192), (np.complex128, 4096)):   # single-stage rings
+    x = rc((2 * 148 + 3, n), dt)
+    p = af.Plan("many", [n], af.C2C if dt == np.complex64 else af.Z2Z, x.shape[0]); assert "ring: G=1 NS=1" in p.describe(), p.describe(); p.destroy()
+    y = af.fft("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
+    e = rel(y, np.fft.fft(x.astype(np.complex128), axis=-1))
+    print("single-stage ring n=%d %s rel %.1e" % (n, np.dtype(dt).name, e), flush=True)
+    assert e < 1e-4
+for dt in (np.complex64, np.complex128):                          # single-buffer TMA column kernel: 1024-point columns, 148+ tiles
+    tl = 16 if dt == np.complex64 else 8
+    x = rc((1024, 150 * tl), dt)
+    p = af.Plan("axis", (1, 1024, 150 * tl), af.C2C if dt == np.complex64 else af.Z2Z)
+    d = p.describe(); p.destroy()
+    xd = torch.from_numpy(x).cuda()
+    y = af.fft2D("Forward", xd).cpu().numpy() if False else None
+    import os
+    os.environ["B200FFT_PIPE"] = "0"; af.lib().accfft_plan_cache_clear()
+    p = af.Plan("axis", (1, 1024, 150 * tl), af.C2C if dt == np.complex64 else af.Z2Z)
+    assert "ring cols" in p.describe(), p.describe()
+    out = torch.empty_like(xd)
+    p.exec(xd, out, af.FORWARD); torch.cuda.synchronize(); p.destroy()
+    os.environ.pop("B200FFT_PIPE"); af.lib().accfft_plan_cache_clear()
+    e = rel(out.cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=0))
+    print("ring cols %s rel %.1e" % (np.dtype(dt).name, e), flush=True)
+    assert e < 1e-4
 x = rc((8192, 128), np.complex64)                                 # band kernel: 4 bands of 32 columns
 p = af.Plan("2d", [8192, 128], af.C2C, 1); assert "band A[" in p.describe(), p.describe(); p.destroy()
 y = af.fft2D("Forward", torch.from_numpy(x).cuda()).cpu().numpy()
