@@ -24,6 +24,6 @@ static KernelEntry make_ringcol_entry() {
 
 void register_ringcol(void (*add)(const KernelEntry&)) {
   add(make_ringcol_entry<RingColCfg<Cfg<float, 1024, 32, 16, 1, 32, 32>>>());       // 512 thr x 128 regs, 128 B runs, 128 KB: cfg5's z axis
-  add(make_ringcol_entry<RingColCfg<Cfg<double, 1024, 16, 8, 1, 16, 16, 4>>>());    // c128: 8 columns (128 B runs), 128 KB
+  add(make_ringcol_entry<RingColCfg<Cfg<double, 1024, 16, 8, 1, 16, 8, 8>>>());     // c128: 8 columns (128 B runs), 128 KB; the radices of the lock-step kernel
 }
 }  // namespace b200fft
