@@ -615,7 +615,11 @@ def main_gpu(args):
                 r = head
             else:
                 try:
-                    r = device_run(c, args, af, torch, None, 1, 0, "strong")
+                    # the side configs are diagnostics beside the headline: at least 10 transforms each, whatever --steps says
+                    # (three transforms of a 15 us kernel measure the launch ramp, not the kernel)
+                    cargs = argparse.Namespace(**vars(args))
+                    cargs.steps = max(args.steps, 10)
+                    r = device_run(c, cargs, af, torch, None, 1, 0, "strong")
                     total_launches += r["launches"]
                 except Exception as ex:
                     configs[c] = {"error": repr(ex)[:300]}
