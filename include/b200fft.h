@@ -143,7 +143,10 @@ enum { B200FFT_SLAB_NATURAL_OUT = 0,               /* out = [D/P][H][W], this ra
 int b200fftPlanSlab3d(b200fftSlabHandle* plan, int64_t d, int64_t h, int64_t w, int type, int rank, int nranks, int flags,
                       b200fftAllgatherFn allgather, void* ctx);
 /* Collective: every rank calls it with the same arguments in the same order.  `scale` multiplies the result in the last
- * pass (1/(D*H*W) for Mode Inverse, FFT.hs:155,172).  `in` is not written; `out` must not alias it. */
+ * pass (1/(D*H*W) for Mode Inverse, FFT.hs:155,172).  `in` is not written; `out` must not alias it.  Unlike b200fftExec, a
+ * slab plan owns per-transform state (receive buffers, barrier epochs): one transform at a time per plan -- calls on one
+ * plan must come from one host thread at a time and are ordered on the device by the library's own barriers.  An error on
+ * one rank (plan creation or exec) leaves the others waiting in the all-gather / at a barrier, as with any collective. */
 int b200fftExecSlab(b200fftSlabHandle plan, const void* in_slab, void* out, int direction, double scale, int layout,
                     b200fftStream stream);
 /* Natural layout: the result is assembled by the peers in a library-owned buffer and then copied to `out`; passing THIS
