@@ -207,6 +207,9 @@ struct Pass {
   const KernelEntry* ringcol = nullptr;
   void* rctws = nullptr;
   int ringcol_ntl = 0, ringcol_grid = 0;
+  const KernelEntry* ringtrans = nullptr;     // ... and its transposing (rows in, line-fastest out) sibling
+  void* rttws = nullptr;
+  int ringtrans_ntl = 0, ringtrans_grid = 0;
   size_t slot_bytes = 0, counter_bytes = 0, counter_off = 0;   // fused / band passes: their share of the plan's band scratch
   void* otw_lo = nullptr;          // outer four-step table (OUTER kernels)
   void* otw_hi = nullptr;
@@ -365,7 +368,8 @@ struct Builder {
     if (flavor == FL_COL) attach_pipe(ps, N, tw4);
     // (not beside the pipelined kernel: for the slab transform's NVLink-bound scatter passes it measured no better than the
     //  lock-step loop kernel -- 8 GPUs 1.92-2.00 ms against 1.93, profiles/r02_slab_cabi.txt)
-    if (flavor == FL_COL && !tw4 && !ps.pipe) attach_ringcol(ps, N);
+    if (flavor == FL_COL && !ps.pipe) attach_ringcol(ps, N, tw4);
+    if (flavor == FL_TRANS && !tw4) attach_ringtrans(ps, N);
     if (flavor == FL_ROW && !tw4) attach_pipe_rows(ps, N);
     push(ps);
     return true;
@@ -388,10 +392,11 @@ struct Builder {
 
   // Column tiles that fill an SM's shared memory (one lock-step CTA per SM, load / butterflies / store in turn): the persistent
   // single-buffer TMA-fed kernel fetches the next tile while the last stage and the stores of the current one run.
-  void attach_ringcol(Pass& ps, long long N) {
+  void attach_ringcol(Pass& ps, long long N, bool tw4) {
     if (getenv("B200FFT_RINGCOL") && atoi(getenv("B200FFT_RINGCOL")) == 0) return;
-    const KernelEntry* q = find_kernel(p->is_double, (int)N, FL_RINGCOL, 0, 0);
-    if (!q || ps.k->smem < 100 * 1024) return;
+    const KernelEntry* q = find_kernel(p->is_double, (int)N, FL_RINGCOL, tw4 ? 1 : 0, 0);
+    // instead of a lock-step tile that fills the SM -- or, for the +tw kernels, one half as wide (128 B runs against 256 B)
+    if (!q || (ps.k->smem < 100 * 1024 && q->TL <= ps.k->TL)) return;
     const Geom& g = ps.g;
     const long long esz = p->is_double ? 16 : 8;
     if (g.nb != 1 || g.ils != 1 || g.ols != 1 || g.nl % q->TL) return;
@@ -407,6 +412,29 @@ struct Builder {
     ps.rctws = make_stage_twiddles(p, q);
     char buf[200];
     snprintf(buf, sizeof buf, " | ring cols: persistent, TMA-fed, one buffer, TL=%d threads=%d smem=%zu tiles=%lld", q->TL, q->threads, q->smem, ntiles);
+    ps.desc += buf;
+  }
+
+  // The transposing last pass of a big four-step through the single-buffer TMA-fed kernel when that makes the store runs longer.
+  void attach_ringtrans(Pass& ps, long long N) {
+    if (getenv("B200FFT_RINGCOL") && atoi(getenv("B200FFT_RINGCOL")) == 0) return;
+    const KernelEntry* q = find_kernel(p->is_double, (int)N, FL_RINGTRANS, 0, 0);
+    if (!q || q->TL <= ps.k->TL) return;
+    const Geom& g = ps.g;
+    const long long esz = p->is_double ? 16 : 8;
+    if (g.ins != 1 || g.ols != 1 || g.nl % q->TL) return;
+    if ((g.ils * esz) % 16 || (g.ios * esz) % 16 || (g.ibs * esz) % 16) return;
+    {
+      const long long tpt = q->N / q->E;
+      if (tpt * g.ons * esz >= (1LL << 32)) return;
+    }
+    const long long ntl = g.nl / q->TL, ntiles = (long long)g.nb * g.no * ntl;
+    if (ntiles < 148 || ntiles >= (1LL << 31)) return;
+    ps.ringtrans = q;
+    ps.ringtrans_ntl = (int)ntl;
+    ps.rttws = make_stage_twiddles(p, q);
+    char buf[200];
+    snprintf(buf, sizeof buf, " | ring trans: persistent, TMA-fed, one buffer, TL=%d threads=%d smem=%zu tiles=%lld", q->TL, q->threads, q->smem, ntiles);
     ps.desc += buf;
   }
 
@@ -1226,6 +1254,17 @@ static int set_func_attrs(b200fft_plan_s* p) {
         ps.ringcol_grid = (int)(grid < ntiles ? grid : ntiles);
       }
     }
+    if (ps.kind == PK_LINES && ps.ringtrans) {
+      int dev = 0, nsm = 0, occ = 0;
+      bool ok = cudaFuncSetAttribute(ps.ringtrans->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.ringtrans->smem) == cudaSuccess &&
+                cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.ringtrans->func, ps.ringtrans->threads, ps.ringtrans->smem) == cudaSuccess && occ > 0;
+      if (!ok) { cudaGetLastError(); ps.ringtrans = nullptr; }
+      else {
+        const long long ntiles = (long long)ps.g.nb * ps.g.no * ps.ringtrans_ntl, grid = (long long)nsm * occ;
+        ps.ringtrans_grid = (int)(grid < ntiles ? grid : ntiles);
+      }
+    }
     if (ps.kind == PK_LINES && ps.ring) {
       int dev = 0, nsm = 0, occ = 0;
       bool ok = cudaFuncSetAttribute(ps.ring->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.ring->smem) == cudaSuccess &&
@@ -1401,7 +1440,7 @@ static bool launch_ringcol(const b200fft_plan_s* p, const Pass& ps, Geom g, cons
   g.ntl = ps.ringcol_ntl;
   float scf = (float)sc;
   double scd = sc;
-  void* args[] = {(void*)&tm, &g, (void*)&dst, (void*)&ps.rctws, p->is_double ? (void*)&scd : (void*)&scf};
+  void* args[] = {(void*)&tm, &g, (void*)&dst, (void*)&ps.rctws, (void*)&ps.tw_lo, (void*)&ps.tw_hi, p->is_double ? (void*)&scd : (void*)&scf};
   static const bool pdl = !(getenv("B200FFT_PDL") && atoi(getenv("B200FFT_PDL")) == 0);
   cudaLaunchConfig_t cfg{};
   const int grid = (max_ctas > 0 && max_ctas < ps.ringcol_grid) ? max_ctas : ps.ringcol_grid;
@@ -1502,6 +1541,31 @@ static int exec_common(b200fftHandle p, const void* in, void* out, int direction
       if (launch_ringcol(p, ps, g, src, dst, sc, 0, stream)) {
         pipe_done = true;
         g_launches.fetch_add(1, std::memory_order_relaxed);
+      }
+    }
+    if (!pipe_done && !rotate && ps.kind == PK_LINES && ps.ringtrans && ((uintptr_t)src & 15) == 0) {
+      Geom g = ps.g;
+      g.swap_in = inverse && first;
+      g.swap_out = inverse && last;
+      g.ntl = ps.ringtrans_ntl;
+      float scf = (float)sc;
+      double scd = sc;
+      void* args[] = {&g, (void*)&src, (void*)&dst, (void*)&ps.rttws, p->is_double ? (void*)&scd : (void*)&scf};
+      static const bool pdl = !(getenv("B200FFT_PDL") && atoi(getenv("B200FFT_PDL")) == 0);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)ps.ringtrans_grid);
+      cfg.blockDim = dim3(ps.ringtrans->threads);
+      cfg.dynamicSmemBytes = ps.ringtrans->smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+      if (cudaLaunchKernelExC(&cfg, ps.ringtrans->func, args) == cudaSuccess) {
+        pipe_done = true;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      } else {
+        cudaGetLastError();
       }
     }
     if (pipe_done) {

@@ -9,7 +9,7 @@ namespace b200fft {
 // FL_PIPE: persistent software-pipelined column kernel, CS = 1 or a cluster (pipe_kernel.cuh)
 // FL_CLUSTER: strided lines of length N = N1*CS transformed by a cluster of CS CTAs (cluster_kernel.cuh)
 // FL_RINGCOL: persistent single-buffer TMA-fed column kernel for tiles that fill an SM (ringcol_kernel.cuh)
-enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4, FL_CLUSTER = 5, FL_PIPE = 6, FL_PIPEROW = 7, FL_CLUSTERROW = 8, FL_RINGCOL = 9 };
+enum Flavor { FL_ROW = 0, FL_COL = 1, FL_TRANS = 2, FL_RING = 3, FL_ROWPAIR = 4, FL_CLUSTER = 5, FL_PIPE = 6, FL_PIPEROW = 7, FL_CLUSTERROW = 8, FL_RINGCOL = 9, FL_RINGTRANS = 10 };
 
 struct KernelEntry {
   int is_double;

@@ -35,9 +35,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 #ifndef B200FFT_RINGCOL_EARLY
 #define B200FFT_RINGCOL_EARLY 0
 #endif
-template <class K_, int EARLY_ = B200FFT_RINGCOL_EARLY>
+template <class K_, bool TW4_ = false, int EARLY_ = B200FFT_RINGCOL_EARLY>
 struct RingColCfg {
   using K = K_;
+  static constexpr bool TW4 = TW4_;     // multiply by the four-step twiddle w_L^(k * line) before the store (first pass of a big 1D)
   static constexpr int THREADS = K::THREADS;
   static constexpr int BOX_ROWS = K::N < 256 ? K::N : 256;          // a TMA box holds at most 256 rows
   static constexpr int NBOX = K::N / BOX_ROWS;
@@ -58,7 +59,8 @@ struct RingColCfg {
 template <class R>
 __global__ void __launch_bounds__(R::THREADS, 1)
 fft_ringcol_kernel(const __grid_constant__ CUtensorMap tm, const Geom g, cpx_t<typename R::K::real>* __restrict__ out,
-                   const cpx_t<typename R::K::real>* __restrict__ tws, typename R::K::real scale) {
+                   const cpx_t<typename R::K::real>* __restrict__ tws, const cpx_t<typename R::K::real>* __restrict__ tw_lo,
+                   const cpx_t<typename R::K::real>* __restrict__ tw_hi, typename R::K::real scale) {
   using K = typename R::K;
   using T = typename K::real;
   using C = cpx_t<T>;
@@ -129,6 +131,24 @@ fft_ringcol_kernel(const __grid_constant__ CUtensorMap tm, const Geom g, cpx_t<t
     if (tid == 0 && k + 1 < nk) issue_last(k + 1);
 
     run_stage<K, K::S - 1>(v, t, tws);
+    if constexpr (R::TW4) {
+      // four-step twiddle w_L^(k * m), k = t + e*TPT, m = the line's multiplier: an anchor per 8 points from the two-level
+      // table and a running product in between (as fft_kernel.cuh)
+      const unsigned m = g.tw_from_o ? (unsigned)o : (unsigned)(lt * K::TL + l) / (unsigned)g.tw_div;
+      const unsigned lomask = (1u << g.tw_lo_bits) - 1u;
+      auto root = [&](unsigned x) { return cmul(__ldg(tw_lo + (x & lomask)), __ldg(tw_hi + (x >> g.tw_lo_bits))); };
+      constexpr int CH = (K::E < 8) ? K::E : 8;
+      const C stepw = root((unsigned)K::TPT * m);
+      static_for<0, K::E / CH>([&](auto qc) {
+        constexpr int q = qc;
+        C w = root((unsigned)(t + q * CH * K::TPT) * m);
+        static_for<0, CH>([&](auto rc) {
+          constexpr int e = q * CH + rc;
+          v[e] = cmul(v[e], w);
+          if constexpr (rc + 1 < CH) w = cmul(w, stepw);
+        });
+      });
+    }
     const T sy = g.swap_out ? -scale : scale;
     if (scale != (T)1 || g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
     const int line = lt * K::TL + l;
@@ -143,6 +163,98 @@ fft_ringcol_kernel(const __grid_constant__ CUtensorMap tm, const Geom g, cpx_t<t
         *reinterpret_cast<C*>(pb + (unsigned long long)(unsigned)e * step_b) = v[e];
       });
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// The transposing last pass of a big four-step (rows in, line-fastest out) the same way: TL contiguous lines of N points land by
+// bulk copies (one per line), are pulled into registers, exchanged in the padded row layout inside the same buffer, and after the
+// last gather -- now with adjacent threads on adjacent LINES -- the buffer goes back to the TMA engine for the next tile while the
+// last stage runs and the results are stored as runs of TL consecutive lines (32 lines = 256 B runs where the lock-step kernel's
+// 64 KB tile has 16 = 128 B; page-scattered 128 B stores reach 4.2 TB/s, 256 B ones 5.6: profiles/r02_scatter_bw.txt).
+template <class K_>
+struct RingTransCfg {
+  using K = K_;
+  static constexpr int THREADS = K::THREADS;
+  static constexpr size_t LINE_BYTES = (size_t)K::N * K::ESZ;
+  static constexpr size_t TILE_BYTES = LINE_BYTES * K::TL;
+  static constexpr size_t BUF_ELEMS = (size_t)K::ROW_ELEMS > (size_t)K::N * K::TL ? (size_t)K::ROW_ELEMS : (size_t)K::N * K::TL;
+  static constexpr size_t BUF_BYTES = ((BUF_ELEMS * K::ESZ + 127) / 128) * 128;
+  static constexpr size_t SMEM = BUF_BYTES + 16;
+  static_assert(K::S >= 2, "the transposing variant needs an exchange to re-map threads");
+  static_assert(SMEM <= 232448, "one SM");
+};
+
+// g: the pass's geometry (ins == 1, ols == 1, nl a multiple of TL); tile = (b, o, lt)
+template <class R>
+__global__ void __launch_bounds__(R::THREADS, 1)
+fft_ringtrans_kernel(const Geom g, const cpx_t<typename R::K::real>* __restrict__ in, cpx_t<typename R::K::real>* __restrict__ out,
+                     const cpx_t<typename R::K::real>* __restrict__ tws, typename R::K::real scale) {
+  using K = typename R::K;
+  using T = typename K::real;
+  using C = cpx_t<T>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + R::BUF_BYTES);
+  const int tid = threadIdx.x;
+  const long long ntiles = (long long)g.nb * g.no * g.ntl;
+  const int nk = ntiles > blockIdx.x ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  auto decode = [&](int k, int& lt, int& o, int& b) {
+    const long long tile = blockIdx.x + (long long)k * gridDim.x;
+    lt = (int)(tile % g.ntl);
+    const long long rest = tile / g.ntl;
+    o = (int)(rest % g.no);
+    b = (int)(rest / g.no);
+  };
+  auto issue = [&](int k) {   // one thread: TL bulk copies, one per line
+    int lt, o, b;
+    decode(k, lt, o, b);
+    const C* base = in + (long long)b * g.ibs + (long long)o * g.ios + (long long)lt * K::TL * g.ils;
+    mbar_expect_tx(full, (uint32_t)R::TILE_BYTES);
+    for (int r = 0; r < K::TL; r++) bulk_g2s(smem_raw + (size_t)r * R::LINE_BYTES, base + (long long)r * g.ils, (uint32_t)R::LINE_BYTES, full);
+  };
+
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (tid == 0) { mbar_init(full, 1); fence_mbar_init(); }
+  __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid == 0 && nk > 0) issue(0);
+
+  for (int k = 0; k < nk; k++) {
+    int lt, o, b;
+    decode(k, lt, o, b);
+    int t = tid % K::TPT, l = tid / K::TPT;          // load mapping: adjacent threads = adjacent points of a line
+    mbar_wait(full, (uint32_t)(k & 1));
+    C v[K::E];
+    static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e] = sm[l * K::N + t + e * K::TPT]; });
+    if (g.swap_in) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].y = -v[e].y; });
+    __syncthreads();   // the dense tile is in registers: the buffer becomes the (padded) exchange space
+    run_stage<K, 0>(v, t, tws);
+    scatter<K, 0, false>(v, sm, l, t);
+    static_for<1, K::S - 1>([&](auto sc) {
+      constexpr int s = sc;
+      __syncthreads();
+      gather<K, false>(v, sm, l, t);
+      run_stage<K, s>(v, t, tws);
+      __syncthreads();
+      scatter<K, s, false>(v, sm, l, t);
+    });
+    __syncthreads();
+    l = tid % K::TL; t = tid / K::TL;                // store mapping: adjacent threads = adjacent lines
+    gather<K, false>(v, sm, l, t);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0 && k + 1 < nk) issue(k + 1);
+
+    run_stage<K, K::S - 1>(v, t, tws);
+    const T sy = g.swap_out ? -scale : scale;
+    if (scale != (T)1 || g.swap_out) static_for<0, K::E>([&](auto ec) { constexpr int e = ec; v[e].x *= scale; v[e].y *= sy; });
+    char* pb = reinterpret_cast<char*>(out + (long long)b * g.obs + (long long)o * g.oos + (long long)(lt * K::TL + l) + (long long)t * g.ons);
+    const unsigned step_b = (unsigned)((long long)K::TPT * g.ons * (long long)sizeof(C));
+    static_for<0, K::E>([&](auto ec) {
+      constexpr int e = ec;
+      *reinterpret_cast<C*>(pb + (unsigned long long)(unsigned)e * step_b) = v[e];
+    });
   }
 }
 
