@@ -310,6 +310,20 @@ def device_run(cfg, args, af, torch, dist, world, rank, scaling_mode, keep_alive
     barrier()
     launches = (af.kernel_launches() - l0) if graph is None else steps * per_step * npass
     ms_total = ev0.elapsed_time(ev1)
+    repeats = 1
+    if graph is not None and getattr(args, "repeat", 1) > 1:
+        # a graph replay of K ~15 us transforms is a ~150 us region: one sample of it is clock-ramp noise (0.67-0.73 run to run).
+        # The side configs take the median of several identical regions.
+        regions = [ms_total]
+        for _ in range(args.repeat - 1):
+            barrier()
+            ev0.record()
+            graph.replay()
+            ev1.record()
+            barrier()
+            regions.append(ev0.elapsed_time(ev1))
+        ms_total = statistics.median(regions)
+        repeats = len(regions)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -325,7 +339,8 @@ def device_run(cfg, args, af, torch, dist, world, rank, scaling_mode, keep_alive
         samples = [ms_step / per_step] * (steps * per_step)
         exec_ms = ms_step / per_step
         how = ("CUDA events around the %d back-to-back transforms of the timed region / %d" % (len(samples), len(samples))) + \
-              ("; the region is one CUDA graph replay (no host dispatch between the launches)" if graph is not None else "")
+              ("; the region is one CUDA graph replay (no host dispatch between the launches)" if graph is not None else "") + \
+              ("; median of %d such regions" % repeats if repeats > 1 else "")
     peak, peak_src = measured_peak()
     alg_bytes = min_passes * 2 * nbytes              # min passes x 2 x N_total x sizeof(complex)
     achieved = alg_bytes / (exec_ms * 1e-3) / 1e9
@@ -619,6 +634,7 @@ def main_gpu(args):
                     # (three transforms of a 15 us kernel measure the launch ramp, not the kernel)
                     cargs = argparse.Namespace(**vars(args))
                     cargs.steps = max(args.steps, 10)
+                    cargs.repeat = 7
                     r = device_run(c, cargs, af, torch, None, 1, 0, "strong")
                     total_launches += r["launches"]
                 except Exception as ex:
