@@ -102,12 +102,19 @@ class ClockSampler:
 
 def dominant_kernel(plan_desc):
     if any("band A[" in d for d in plan_desc):
-        return "fft_band_kernel (+ fft_lines_kernel rows)"
+        return "fft_band_kernel (+ fft_ring_rows_kernel rows)"
+    names = []
     if any("| ring:" in d for d in plan_desc):
-        return "fft_ring_rows_kernel"
+        names.append("fft_ring_rows_kernel")
     if any("| pipe" in d for d in plan_desc):
-        return "fft_lines_kernel + fft_pipe_cols_kernel"
-    return "fft_lines_kernel"
+        names.append("fft_pipe_cols_kernel")
+    if any("| ring cols" in d for d in plan_desc):
+        names.append("fft_ringcol_kernel")
+    if any("| ring trans" in d for d in plan_desc):
+        names.append("fft_ringtrans_kernel")
+    if any("|" not in d for d in plan_desc) or not names:
+        names.insert(0, "fft_lines_kernel")
+    return " + ".join(names)
 
 
 def flops_of(cfg, batch):
