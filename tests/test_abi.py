@@ -123,3 +123,32 @@ def test_plain_c_host_computes_a_correct_transform(tmp_path):
     exe = _build_c_smoke(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "max abs error" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_slab_entry_point_validates_before_touching_a_device():
+    """b200fftPlanSlab3d (the multi-GPU entry point): argument errors are reported as such with or without a GPU; a valid
+    request on a box without a device is B200FFT_NO_DEVICE -- there is no host path behind this entry either."""
+    import torch
+    from accelerate_fft_b200._lib import ALLGATHER_FN, lib
+    L = lib()
+    calls = []
+
+    def allgather(_ctx, send, recv, nbytes):
+        calls.append(nbytes)
+        ctypes.memmove(recv, send, nbytes)
+        return 0
+
+    cb = ALLGATHER_FN(allgather)
+    h = ctypes.c_void_p()
+    C2C = 0x29
+    assert L.b200fftPlanSlab3d(ctypes.byref(h), 64, 64, 64, C2C, 0, 0, 0, cb, None) == 4        # nranks < 1: INVALID_VALUE
+    assert L.b200fftPlanSlab3d(ctypes.byref(h), 64, 64, 64, C2C, 2, 2, 0, cb, None) == 4        # rank out of range
+    assert L.b200fftPlanSlab3d(ctypes.byref(h), 64, 64, 64, 0x2a, 0, 1, 0, cb, None) == 3       # not C2C / Z2Z: INVALID_TYPE
+    assert L.b200fftPlanSlab3d(ctypes.byref(h), 64, 63, 64, C2C, 0, 2, 0, cb, None) == 8        # H not divisible: INVALID_SIZE
+    assert L.b200fftPlanSlab3d(ctypes.byref(h), 48, 32, 16, C2C, 0, 1, 0, cb, None) == 16       # D not a power of two: NOT_SUPPORTED
+    assert L.b200fftPlanSlab3d(ctypes.byref(h), 4096, 64, 64, C2C, 0, 1, 0, cb, None) == 16     # D above the scatter pass's reach
+    assert not calls                                                                            # nothing was exchanged for a bad request
+    if not torch.cuda.is_available():
+        assert L.b200fftPlanSlab3d(ctypes.byref(h), 64, 64, 64, C2C, 0, 1, 1, cb, None) == 11   # NO_DEVICE
+    assert L.b200fftExecSlab(None, None, None, -1, 1.0, 0, None) == 1                           # INVALID_PLAN
+    assert L.b200fftDestroySlab(None) == 1
