@@ -126,6 +126,43 @@ def flops_of(cfg, batch):
     return per * (2 if cfg == "cfg2" else 1)      # cfg2's step is Forward + Inverse
 
 
+def workload_geometry(cfg, world, scaling_mode):
+    """How one config is laid over `world` ranks: (replicas, rows per rank, scaling label, per-rank shape, bytes per
+    buffer, rotating buffers).  Pure arithmetic -- both arms describe the workload with it."""
+    kind, dims, dtp, batch, _, _ = CONFIGS[cfg]
+    esz = 8 if dtp == "c64" else 16
+    if cfg in ("cfg3", "cfg4", "cfg5") and world > 1:
+        # BASELINE.json names these single-GPU (cfg5's multi-GPU form is the slab transform, reported under "slab")
+        replicas, my_batch, scaling = world, 1, "weak"
+    else:
+        if batch % world:
+            raise SystemExit("batch %d not divisible by %d ranks" % (batch, world))
+        if scaling_mode == "strong":      # BASELINE's rows split over the ranks ("2 @ P": [65536/P, 4096] per GPU)
+            replicas, my_batch, scaling = 1, batch // world, "strong"
+        else:                             # every rank transforms a full BASELINE batch of its own
+            replicas, my_batch, scaling = world, batch, "weak"
+    shape = ((my_batch,) + dims) if kind == "fft" else dims
+    n_local = 1
+    for d in shape:
+        n_local *= d
+    nbytes = n_local * esz
+    # several distinct buffer pairs when one fits in L2 (cfg1): rotate so every step streams from HBM
+    nbuf = 1 if nbytes * 2 > 4 * 126e6 else int(math.ceil(4 * 126e6 / (2 * nbytes)))
+    return replicas, my_batch, scaling, shape, nbytes, nbuf
+
+
+def config_object(cfg, world, scaling_mode):
+    """The `config` key of the JSON line: identical in the b200 arm and the --impl reference arm (same workload, same
+    sharding); what the reference arm actually samples of it is said in its cpu_baseline.sample."""
+    kind, dims, dtp, batch, _, desc = CONFIGS[cfg]
+    _, my_batch, scaling, shape, nbytes, nbuf = workload_geometry(cfg, world, scaling_mode)
+    return {"workload": desc, "per_gpu_shape": list(shape),
+            "sharding": ("the batch rows are the units: every rank owns %d of the %d rows, no data-path collective"
+                         % (my_batch, my_batch * world if scaling == "weak" else batch)) if kind == "fft" else "independent replicas",
+            "l2": "inputs larger than L2 (%.0f MB per buffer x %d rotating buffers)" % (nbytes / 1e6, nbuf),
+            "inverse_scale": "fused into the last pass", "step": "Forward+Inverse" if cfg == "cfg2" else "Forward"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's CPU path
 # ------------------------------------------------------------------------------------------------
@@ -202,9 +239,10 @@ def main_reference(args):
     kind, dims, dtp, batch, _, desc = CONFIGS[cfg]
     line = {
         "impl": "reference", "metric": "fft_gflops_5nlog2n", "value": base["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": workload_geometry(cfg, max(1, args.gpus), args.scaling)[2],
         "vs_baseline": None, "dtype": "f64" if dtp == "c128" else "f32", "data": "synthetic",
-        "config": {"workload": desc, "sample": base["sample"]},
+        "config": config_object(cfg, max(1, args.gpus), args.scaling),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference's own bindings need GHC + FFTW/cuFFT (absent here): this arm is the oracle port of its pure-Accelerate CPU path",
@@ -226,24 +264,8 @@ def device_run(cfg, args, af, torch, dist, world, rank, scaling_mode, keep_alive
     kind, dims, dtp, batch, min_passes, desc = CONFIGS[cfg]
     dt = torch.complex64 if dtp == "c64" else torch.complex128
     esz = 8 if dtp == "c64" else 16
-    if cfg in ("cfg3", "cfg4", "cfg5") and world > 1:
-        # BASELINE.json names these single-GPU (cfg5's multi-GPU form is the slab transform, reported under "slab")
-        replicas, my_batch, scaling = world, 1, "weak"
-    else:
-        if batch % world:
-            raise SystemExit("batch %d not divisible by %d ranks" % (batch, world))
-        if scaling_mode == "strong":      # BASELINE's rows split over the ranks ("2 @ P": [65536/P, 4096] per GPU)
-            replicas, my_batch, scaling = 1, batch // world, "strong"
-        else:                             # every rank transforms a full BASELINE batch of its own
-            replicas, my_batch, scaling = world, batch, "weak"
-    shape = ((my_batch,) + dims) if kind == "fft" else dims
-    n_local = 1
-    for s in shape:
-        n_local *= s
+    replicas, my_batch, scaling, shape, nbytes, nbuf = workload_geometry(cfg, world, scaling_mode)
     torch.manual_seed(1000 + int(cfg[3]) + 7919 * rank)
-    nbytes = n_local * esz
-    # several distinct buffer pairs when one fits in L2 (cfg1): rotate so every step streams from HBM
-    nbuf = 1 if nbytes * 2 > 4 * 126e6 else int(math.ceil(4 * 126e6 / (2 * nbytes)))
     xs = [torch.view_as_complex(torch.rand(shape + (2,), dtype=torch.float32 if dtp == "c64" else torch.float64, device="cuda") * 2 - 1)
           for _ in range(nbuf)]
     plan_kind = {"fft": "many", "fft1D": "1d", "fft2D": "2d", "fft3D": "3d"}[kind]
@@ -675,10 +697,7 @@ def main_gpu(args):
             "metric": "fft_gflops_5nlog2n", "value": head["value"], "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64" if dtp == "c128" else "f32", "data": "synthetic",
-            "config": {"workload": desc, "per_gpu_shape": list(shape), "sharding": ("the batch rows are the units: every rank owns %d of the %d rows, no data-path collective" % (my_batch, my_batch * world if scaling == "weak" else batch))
-                                   if kind == "fft" else "independent replicas",
-                       "l2": "inputs larger than L2 (%.0f MB per buffer x %d rotating buffers)" % (nbytes / 1e6, nbuf),
-                       "inverse_scale": "fused into the last pass", "step": "Forward+Inverse" if cfg == "cfg2" else "Forward"},
+            "config": config_object(cfg, world, args.scaling),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(total_launches), "clocks": clocks,
             "hbm_gbs_whole_step": (2 if cfg == "cfg2" else 1) * alg_bytes * world / (ms_step * 1e-3) / 1e9,
         }
