@@ -196,7 +196,7 @@ __device__ __forceinline__ void small_dft(C* a) {
     dft<R>(v);                                             // cplx.cuh: radix-4 recursion, compile-time constants
     static_for<0, R>([&](auto ic) { constexpr int i = ic; a[i] = v[i]; });
   } else {
-    // odd primes 7, 11, 13: pairs (r, R-r) share cos / sin sums -- (R-1)^2 / 2 real multiplies, all compile-time roots
+    // odd primes 7 ... 31: pairs (r, R-r) share cos / sin sums -- (R-1)^2 / 2 real multiplies, all compile-time roots
     constexpr int H = (R - 1) / 2;
     C t[H], d[H];
     static_for<0, H>([&](auto ic) { constexpr int i = ic; t[i] = cadd(a[i + 1], a[R - 1 - i]); d[i] = csub(a[i + 1], a[R - 1 - i]); });
@@ -254,7 +254,9 @@ __device__ __noinline__ void mixed_stage(const C* __restrict__ src, C* __restric
   }
 }
 
-template <typename C>
+// BIGP: the instance that also holds the prime radices 17 ... 31 (their butterflies need more registers: a separate kernel
+// instance, so the register allocation -- and with it the occupancy -- of every other length stays what it was)
+template <typename C, bool BIGP>
 __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, const C* gin, C* gout, const C* tw, int N, int Ns,
                                                 unsigned magic, int tl, int tpl, int swap_in, int swap_out, real_of<C> scale) {
 #define MS_CASE(r) case r: mixed_stage<r>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
@@ -263,19 +265,33 @@ __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, con
       MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6) MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12) MS_CASE(13)
       MS_CASE(14) MS_CASE(15) MS_CASE(16) MS_CASE(18) MS_CASE(20) MS_CASE(21) MS_CASE(24) MS_CASE(25) MS_CASE(27) MS_CASE(28) MS_CASE(30)
       MS_CASE(32)
-      default: break;
+      default:
+        if constexpr (BIGP) {
+          switch (R) {
+            MS_CASE(17) MS_CASE(19) MS_CASE(23) MS_CASE(29) MS_CASE(31)      // prime radices: see factor_small
+            default: break;
+          }
+        }
+        break;
     }
-  } else {   // c128: at most 16 values per thread
+  } else {   // c128: at most 16 values per thread -- and the primes 17, 19, 23, whose pair sums fit the 255 registers of a 256-thread CTA
     switch (R) {
       MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6) MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12) MS_CASE(13)
       MS_CASE(14) MS_CASE(15) MS_CASE(16)
-      default: break;
+      default:
+        if constexpr (BIGP) {
+          switch (R) {
+            MS_CASE(17) MS_CASE(19) MS_CASE(23)
+            default: break;
+          }
+        }
+        break;
     }
   }
 #undef MS_CASE
 }
 
-template <typename C>
+template <typename C, bool BIGP = false>
 __global__ void __launch_bounds__(sizeof(C) == 8 ? 512 : 256)
 mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw, real_of<C> scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,7 +316,7 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
       const int R = p.radix[s];
       const bool first = s == 0, last = s + 1 == p.nstages;
       if (live) {
-        mixed_stage_any(R, (const C*)src, dst, first ? gin : (const C*)nullptr, last ? gout : (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl,
+        mixed_stage_any<C, BIGP>(R, (const C*)src, dst, first ? gin : (const C*)nullptr, last ? gout : (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl,
                         p.swap_in, p.swap_out, scale);
       }
       if (!last) __syncthreads();
@@ -331,7 +347,7 @@ mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict_
   C* dst = buf1 + l * pitch;
   int Ns = 1;
   for (int s = 0; s < p.nstages; s++) {
-    mixed_stage_any(p.radix[s], (const C*)src, dst, (const C*)nullptr, (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl, 0, 0, scale);
+    mixed_stage_any<C, BIGP>(p.radix[s], (const C*)src, dst, (const C*)nullptr, (C*)nullptr, tw, N, Ns, p.magic_ns[s], tl, tpl, 0, 0, scale);
     __syncthreads();
     C* t = src; src = dst; dst = t;
     Ns *= p.radix[s];
@@ -430,12 +446,25 @@ static const size_t kBluesteinWorkspaceCap = 512ull << 20;  // per buffer
 
 // Fewest Stockham stages over the radices a thread can hold (c64: up to 32 values, c128: up to 16); among equal counts
 // the most balanced product; odd radices first (the first stage has no twiddles and an odd store stride).
-static bool factor_small(long long n, std::vector<int>* f, int rmax) {
-  static const int kRad[] = {32, 30, 28, 27, 25, 24, 21, 20, 18, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+// Prime factors 17 ... 31 (c128: 17, 19, 23) are radices of their own -- the pair-sum butterfly of small_dft costs ~R/2
+// multiply-adds per point, far below what the line's HBM traffic leaves room for -- so a length like 34, 323 or 961 takes the
+// one-pass mixed-radix kernel instead of Bluestein's two 4N-point transforms (191 of the 992 lengths in [33, 1024], the range
+// the reference's suite draws from, test/Test/Base.hs:44-45).  B200FFT_MAX_PRIME=13 restores the round-1 behaviour.
+static int max_prime_radix(int is_double) {
+  int cap = is_double ? 23 : 31;
+  if (const char* e = getenv("B200FFT_MAX_PRIME")) { const int v = atoi(e); if (v >= 13 && v < cap) cap = v; }
+  return cap;
+}
+static bool factor_small(long long n, std::vector<int>* f, int rmax, int pmax) {
+  static const int kRad[] = {32, 31, 30, 29, 28, 27, 25, 24, 23, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+  auto big_prime = [](int r) { return r == 17 || r == 19 || r == 23 || r == 29 || r == 31; };
   f->clear();
   {
     long long m = n;
-    for (int pr : {2, 3, 5, 7, 11, 13}) while (m % pr == 0) m /= pr;
+    for (int pr : {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31}) {
+      if (pr > 13 && pr > pmax) break;
+      while (m % pr == 0) m /= pr;
+    }
     if (m != 1) return false;
   }
   if (n >= (1LL << 20)) return false;
@@ -448,7 +477,8 @@ static bool factor_small(long long n, std::vector<int>* f, int rmax) {
     if (memo[(size_t)m].stages >= 0) return memo[(size_t)m];
     Best best{1 << 20, 1 << 20, 0};
     for (int r : kRad) {
-      if (r > rmax || m % r) continue;
+      if (big_prime(r) ? r > pmax : r > rmax) continue;
+      if (m % r) continue;
       const Best c = go(m / r);
       if (c.stages >= (1 << 20)) continue;
       const int st = c.stages + 1, mx = c.maxrad > r ? c.maxrad : r;
@@ -489,7 +519,13 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
     return 0;
   }
   std::vector<int> f;
-  const bool smooth = N < (1LL << 20) && factor_small(N, &f, is_double ? 16 : 32);
+  bool smooth = N < (1LL << 20) && factor_small(N, &f, is_double ? 16 : 32, max_prime_radix(is_double));
+  if (smooth && f.size() > 2) {
+    // a prime radix of 17 ... 31 pays in one- and two-stage plans (34: 21 -> 54 %, 323: 22 -> 45 %, 841: 26 -> 39 % of the HBM
+    // roofline against Bluestein); with three stages it does not (986: 30 -> 30 %, 1023: 30 -> 25 %): those stay on Bluestein
+    // (profiles/r02_non_pow2_prime_radix.txt)
+    for (int r : f) if (r == 17 || r == 19 || r == 23 || r == 29 || r == 31) smooth = false;
+  }
   if (smooth && ((size_t)N + N / 32 + 1) * esz * 2 <= kMixedSmemCap && N < 65536 && f.size() <= 12) {
     gp->bluestein = 0;
     gp->nstages = (int)f.size();
@@ -644,7 +680,10 @@ static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst,
     // the caller folds first/last-pass information into `inverse`: see launch_generic
     mp.swap_in = inverse & 1; mp.swap_out = (inverse >> 1) & 1;
     const long long tiles = (gp.lines + gp.TL - 1) / gp.TL;
-    mixed_radix_kernel<C><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
+    bool bigp = false;
+    for (int i = 0; i < gp.nstages; i++) bigp = bigp || gp.radix[i] == 17 || gp.radix[i] == 19 || gp.radix[i] == 23 || gp.radix[i] == 29 || gp.radix[i] == 31;
+    if (bigp) mixed_radix_kernel<C, true><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
+    else mixed_radix_kernel<C, false><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
     *nl += 1;
     return cudaGetLastError();
   }
@@ -765,9 +804,11 @@ cudaError_t launch_centre(int is_double, const void* src, void* dst, long long d
 int generic_set_attrs() {
   cudaFuncSetAttribute(tiny_dft_kernel<float2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   cudaFuncSetAttribute(tiny_dft_kernel<double2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  if (cudaFuncSetAttribute(mixed_radix_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
+  if (cudaFuncSetAttribute(mixed_radix_kernel<float2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
+      cudaFuncSetAttribute(mixed_radix_kernel<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;
-  if (cudaFuncSetAttribute(mixed_radix_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
+  if (cudaFuncSetAttribute(mixed_radix_kernel<double2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
+      cudaFuncSetAttribute(mixed_radix_kernel<double2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;
   return 0;
 }
