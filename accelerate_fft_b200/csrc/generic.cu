@@ -256,7 +256,8 @@ __device__ __noinline__ void mixed_stage(const C* __restrict__ src, C* __restric
 
 // BIGP: the instance that also holds the prime radices 17 ... 31 (their butterflies need more registers: a separate kernel
 // instance, so the register allocation -- and with it the occupancy -- of every other length stays what it was)
-template <typename C, bool BIGP>
+// BIGP = 2 (c64 only): also the primes 37 ... 61, in CTAs of at most 256 threads (255 registers per thread)
+template <typename C, int BIGP>
 __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, const C* gin, C* gout, const C* tw, int N, int Ns,
                                                 unsigned magic, int tl, int tpl, int swap_in, int swap_out, real_of<C> scale) {
 #define MS_CASE(r) case r: mixed_stage<r>(src, dst, gin, gout, tw, N, Ns, magic, tl, tpl, swap_in, swap_out, scale); break;
@@ -266,10 +267,17 @@ __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, con
       MS_CASE(14) MS_CASE(15) MS_CASE(16) MS_CASE(18) MS_CASE(20) MS_CASE(21) MS_CASE(24) MS_CASE(25) MS_CASE(27) MS_CASE(28) MS_CASE(30)
       MS_CASE(32)
       default:
-        if constexpr (BIGP) {
+        if constexpr (BIGP >= 1) {
           switch (R) {
             MS_CASE(17) MS_CASE(19) MS_CASE(23) MS_CASE(29) MS_CASE(31)      // prime radices: see factor_small
-            default: break;
+            default:
+              if constexpr (BIGP >= 2) {
+                switch (R) {
+                  MS_CASE(37) MS_CASE(41) MS_CASE(43) MS_CASE(47) MS_CASE(53) MS_CASE(59) MS_CASE(61)
+                  default: break;
+                }
+              }
+              break;
           }
         }
         break;
@@ -279,7 +287,7 @@ __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, con
       MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6) MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12) MS_CASE(13)
       MS_CASE(14) MS_CASE(15) MS_CASE(16)
       default:
-        if constexpr (BIGP) {
+        if constexpr (BIGP >= 1) {
           switch (R) {
             MS_CASE(17) MS_CASE(19) MS_CASE(23)
             default: break;
@@ -291,8 +299,8 @@ __device__ __forceinline__ void mixed_stage_any(int R, const C* src, C* dst, con
 #undef MS_CASE
 }
 
-template <typename C, bool BIGP = false>
-__global__ void __launch_bounds__(sizeof(C) == 8 ? 512 : 256)
+template <typename C, int BIGP = 0>
+__global__ void __launch_bounds__((sizeof(C) == 8 && BIGP < 2) ? 512 : 256)
 mixed_radix_kernel(const MixedParams p, const C* __restrict__ in, C* __restrict__ out, const C* __restrict__ tw, real_of<C> scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = (int)p.N, TL = p.TL, tpl = 1 << p.tpl_log2;
@@ -446,22 +454,22 @@ static const size_t kBluesteinWorkspaceCap = 512ull << 20;  // per buffer
 
 // Fewest Stockham stages over the radices a thread can hold (c64: up to 32 values, c128: up to 16); among equal counts
 // the most balanced product; odd radices first (the first stage has no twiddles and an odd store stride).
-// Prime factors 17 ... 31 (c128: 17, 19, 23) are radices of their own -- the pair-sum butterfly of small_dft costs ~R/2
+// Prime factors 17 ... 61 (c128: 17, 19, 23) are radices of their own -- the pair-sum butterfly of small_dft costs ~R/2
 // multiply-adds per point, far below what the line's HBM traffic leaves room for -- so a length like 34, 323 or 961 takes the
 // one-pass mixed-radix kernel instead of Bluestein's two 4N-point transforms (191 of the 992 lengths in [33, 1024], the range
 // the reference's suite draws from, test/Test/Base.hs:44-45).  B200FFT_MAX_PRIME=13 restores the round-1 behaviour.
 static int max_prime_radix(int is_double) {
-  int cap = is_double ? 23 : 31;
+  int cap = is_double ? 23 : 61;
   if (const char* e = getenv("B200FFT_MAX_PRIME")) { const int v = atoi(e); if (v >= 13 && v < cap) cap = v; }
   return cap;
 }
 static bool factor_small(long long n, std::vector<int>* f, int rmax, int pmax) {
-  static const int kRad[] = {32, 31, 30, 29, 28, 27, 25, 24, 23, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
-  auto big_prime = [](int r) { return r == 17 || r == 19 || r == 23 || r == 29 || r == 31; };
+  static const int kRad[] = {61, 59, 53, 47, 43, 41, 37, 32, 31, 30, 29, 28, 27, 25, 24, 23, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+  auto big_prime = [](int r) { return r == 17 || r == 19 || r == 23 || r == 29 || r == 31 || r >= 37; };
   f->clear();
   {
     long long m = n;
-    for (int pr : {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31}) {
+    for (int pr : {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61}) {
       if (pr > 13 && pr > pmax) break;
       while (m % pr == 0) m /= pr;
     }
@@ -524,7 +532,7 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
     // a prime radix of 17 ... 31 pays in one- and two-stage plans (34: 21 -> 54 %, 323: 22 -> 45 %, 841: 26 -> 39 % of the HBM
     // roofline against Bluestein); with three stages it does not (986: 30 -> 30 %, 1023: 30 -> 25 %): those stay on Bluestein
     // (profiles/r02_non_pow2_prime_radix.txt)
-    for (int r : f) if (r == 17 || r == 19 || r == 23 || r == 29 || r == 31) smooth = false;
+    for (int r : f) if (r == 17 || r == 19 || r == 23 || r == 29 || r == 31 || r >= 37) smooth = false;
   }
   if (smooth && ((size_t)N + N / 32 + 1) * esz * 2 <= kMixedSmemCap && N < 65536 && f.size() <= 12) {
     gp->bluestein = 0;
@@ -538,7 +546,7 @@ int plan_generic_axis(int is_double, long long O, long long N, long long I, Gene
     for (int r : f) rbig = r > rbig ? r : rbig;
     int tl2 = 0;
     while ((2 << tl2) <= N / rbig && tl2 < 8) tl2++;
-    const int tmax = is_double ? 256 : 512;
+    const int tmax = (is_double || rbig > 32) ? 256 : 512;     // (the instance holding the primes 37 ... 61 is built for 256 threads)
     int want = I > 1 ? 8 : 4;
     while ((want << tl2) < 64) want *= 2;
     int TL = (int)((I > 1 ? kMixedSmemCap : (size_t)(64 * 1024)) / line_bytes);
@@ -680,10 +688,22 @@ static cudaError_t launch_generic_t(const GenericPass& gp, const C* src, C* dst,
     // the caller folds first/last-pass information into `inverse`: see launch_generic
     mp.swap_in = inverse & 1; mp.swap_out = (inverse >> 1) & 1;
     const long long tiles = (gp.lines + gp.TL - 1) / gp.TL;
-    bool bigp = false;
-    for (int i = 0; i < gp.nstages; i++) bigp = bigp || gp.radix[i] == 17 || gp.radix[i] == 19 || gp.radix[i] == 23 || gp.radix[i] == 29 || gp.radix[i] == 31;
-    if (bigp) mixed_radix_kernel<C, true><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
-    else mixed_radix_kernel<C, false><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
+    int bigp = 0;
+    for (int i = 0; i < gp.nstages; i++) {
+      const int r = gp.radix[i];
+      if (r > 32) bigp = 2;
+      else if ((r == 17 || r == 19 || r == 23 || r == 29 || r == 31) && bigp < 1) bigp = 1;
+    }
+    if constexpr (sizeof(C) == 8) {
+      if (bigp == 2) {
+        mixed_radix_kernel<C, 2><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
+        *nl += 1;
+        return cudaGetLastError();
+      }
+    }
+    if (bigp == 2) return cudaErrorInvalidValue;     // (the planner never gives c128 a radix above 23)
+    if (bigp) mixed_radix_kernel<C, 1><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
+    else mixed_radix_kernel<C, 0><<<(unsigned)tiles, gp.threads, gp.smem, stream>>>(mp, src, dst, (const C*)gp.tw, (T)scale);
     *nl += 1;
     return cudaGetLastError();
   }
@@ -804,11 +824,12 @@ cudaError_t launch_centre(int is_double, const void* src, void* dst, long long d
 int generic_set_attrs() {
   cudaFuncSetAttribute(tiny_dft_kernel<float2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   cudaFuncSetAttribute(tiny_dft_kernel<double2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  if (cudaFuncSetAttribute(mixed_radix_kernel<float2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
-      cudaFuncSetAttribute(mixed_radix_kernel<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
+  if (cudaFuncSetAttribute(mixed_radix_kernel<float2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
+      cudaFuncSetAttribute(mixed_radix_kernel<float2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
+      cudaFuncSetAttribute(mixed_radix_kernel<float2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;
-  if (cudaFuncSetAttribute(mixed_radix_kernel<double2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
-      cudaFuncSetAttribute(mixed_radix_kernel<double2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
+  if (cudaFuncSetAttribute(mixed_radix_kernel<double2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess ||
+      cudaFuncSetAttribute(mixed_radix_kernel<double2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixedSmemCap) != cudaSuccess)
     return B200FFT_INTERNAL_ERROR;
   return 0;
 }

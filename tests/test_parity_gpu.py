@@ -125,32 +125,33 @@ def test_fft_every_length_1_to_130_and_reference_range(af, oracle, dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode", MODES)
-def test_prime_radices_17_to_31_one_pass(af, oracle, dtype, mode):
-    """Lengths whose largest prime factor is 17 ... 31 (c128: 17, 19, 23) take the one-pass mixed-radix kernel with a prime
+def test_prime_radices_17_to_61_one_pass(af, oracle, dtype, mode):
+    """Lengths whose largest prime factor is 17 ... 61 (c128: 17, 19, 23) take the one-pass mixed-radix kernel with a prime
     radix of their own instead of Bluestein (generic.cu factor_small): rows against the exact DFT, strided axes through
-    fft2D / fft3D against numpy float64; 191 of the 992 lengths the reference's suite draws from (test/Test/Base.hs:44-45)."""
+    fft2D / fft3D against numpy float64; a third of the 992 lengths the reference's suite draws from (test/Test/Base.hs:44-45)."""
     rng = np.random.default_rng(21)
     lens = [34, 38, 46, 58, 62, 17 * 17, 17 * 19, 19 * 23, 23 * 29, 29 * 29, 31 * 31, 3 * 17 * 19, 2 * 17 * 29, 4 * 13 * 19, 1023,
-            8 * 31, 32 * 23, 5 * 7 * 29]
+            8 * 31, 32 * 23, 5 * 7 * 29, 37, 41, 43, 47, 53, 59, 61, 2 * 37, 37 * 24, 61 * 16, 53 * 19, 47 * 17, 43 * 23, 41 * 25,
+            59 * 13, 3 * 5 * 37, 37 * 41]
     sgn = -1 if mode == "Forward" else 1
     for n in lens:
         p = af.Plan("many", [n], af.C2C if dtype == np.complex64 else af.Z2Z, 5)
         d = p.describe()
         p.destroy()
         # ... when one or two stages do it (with three the measured gain is gone: those lengths stay on Bluestein)
-        rad = ({2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 21, 24, 25, 27, 28, 30, 32, 17, 19, 23, 29, 31}
-               if dtype == np.complex64 else set(range(2, 17)) | {17, 19, 23})
+        rad = ({2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 21, 24, 25, 27, 28, 30, 32, 17, 19, 23, 29, 31,
+                37, 41, 43, 47, 53, 59, 61} if dtype == np.complex64 else set(range(2, 17)) | {17, 19, 23})
         two_stage = n in rad or any(n % a == 0 and n // a in rad for a in rad)
         assert ("mixed-radix" in d) == two_stage, (n, d)
         x = rand_complex(rng, (5, n), dtype)
         ex = oracle.exact_dft(sgn, x).astype(np.complex128) / (n if mode == "Inverse" else 1)
         assert rel_l2(gpu(af, "fft", mode, x), ex) <= bar(dtype, n), (n, mode)
-    for shape in [(34, 57), (323, 40), (96, 17 * 23), (31, 31)]:
+    for shape in [(34, 57), (323, 40), (96, 17 * 23), (31, 31), (37, 41), (2 * 53, 61 * 4)]:
         x = rand_complex(rng, shape, dtype)
         x128 = x.astype(np.complex128)
         ex = np.fft.fft2(x128) if mode == "Forward" else np.fft.ifft2(x128) * (1 if mode == "Inverse" else x.size)
         assert rel_l2(gpu(af, "fft2D", mode, x), ex) <= bar(dtype, x.size), (shape, mode)
-    for shape in [(17, 19, 23), (34, 6, 58)]:
+    for shape in [(17, 19, 23), (34, 6, 58), (37, 5, 47)]:
         x = rand_complex(rng, shape, dtype)
         x128 = x.astype(np.complex128)
         ex = np.fft.fftn(x128) if mode == "Forward" else np.fft.ifftn(x128) * (1 if mode == "Inverse" else x.size)
