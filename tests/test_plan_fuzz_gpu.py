@@ -41,6 +41,7 @@ def test_switch_point_shapes(af):
     assert not failures, failures
 
 
+@pytest.mark.timeout(180, method="thread")     # a wedged stream must end the process, not hold the box
 def test_concurrent_host_threads_share_plans(af):
     """SURVEY.md 8(b) threading: GHC runs callers on different OS threads; plan creation is serialised per cache
     (PTX/Plans.hs:71) but exec is not (:86), so exec must be re-entrant on a shared plan -- here six host threads, each on
